@@ -1,0 +1,107 @@
+"""Synthetic forest tiles (SURVEY.md §8d generator spec) -- the bench/test workload.
+
+There is no network for the L1W data, so BASELINE.json's configs are quoted on these tiles:
+ground sheet + trunks (cylinder surfaces) + noisy branches, down-sampled to one point per 0.1 m
+voxel (what `generate_tiles` does with open3d, tree_learn/util/pipeline.py:43-46), rounded to
+2 decimals and xy-centred.  Output mirrors `TreeDataset.collate_fn`
+(tree_learn/dataset/dataset.py:214-226).
+"""
+import numpy as np
+import torch
+
+TREE_CLASS, NON_TREE_CLASS = 0, 1   # tree_learn/dataset/dataset.py:9-10
+
+
+def synth_forest(edge=20.0, height=20.0, n_trees=20, seed=0, voxel=0.1, ground_density=1000.0):
+    """Returns dict(coords f32 [N,3] centred, feat f32 [N] verticality, inst i64 [N] (0 = ground),
+    base f32 [N,3] tree-base position per point, n_raw)."""
+    rng = np.random.default_rng(seed)
+    pts, inst, vert, base = [], [], [], []
+
+    def ground_z(x, y):
+        return 1.0 + 0.3 * np.sin(x / 3.0) + 0.3 * np.cos(y / 4.0)
+
+    ng = int(ground_density * edge * edge)
+    gx, gy = rng.uniform(0, edge, ng), rng.uniform(0, edge, ng)
+    pts.append(np.stack([gx, gy, ground_z(gx, gy) + rng.normal(0, 0.03, ng)], 1))
+    inst.append(np.zeros(ng, np.int64))
+    vert.append(rng.uniform(0, 1, ng))
+    base.append(np.zeros((ng, 3)))
+    for t in range(n_trees):
+        cx, cy = rng.uniform(1, edge - 1, 2)
+        h = rng.uniform(10, 18)
+        r = rng.uniform(0.1, 0.3)
+        b = np.array([cx, cy, ground_z(cx, cy)])
+        nt = int(400 * h)
+        ang = rng.uniform(0, 2 * np.pi, nt)
+        tz = rng.uniform(1.0, 0.6 * h, nt)
+        pts.append(np.stack([cx + r * np.cos(ang), cy + r * np.sin(ang), tz], 1))
+        inst.append(np.full(nt, t + 1, np.int64))
+        vert.append(rng.uniform(0.7, 1.0, nt))
+        base.append(np.broadcast_to(b, (nt, 3)))
+        nb, npb = 40, 300
+        d = rng.normal(size=(nb, 3))
+        d[:, 2] = np.abs(d[:, 2]) * 0.4
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        length = rng.uniform(1.0, 3.5, nb)
+        z0 = rng.uniform(0.4 * h, h, nb)
+        s = rng.uniform(0, 1, (nb, npb)) * length[:, None]
+        p = np.stack([cx + s * d[:, None, 0], cy + s * d[:, None, 1], z0[:, None] + s * d[:, None, 2]], 2)
+        p = p + rng.normal(size=p.shape) * (0.08 * (0.3 + s / length[:, None]))[:, :, None]
+        p = p.reshape(-1, 3)
+        pts.append(p)
+        inst.append(np.full(len(p), t + 1, np.int64))
+        vert.append(rng.uniform(0, 1, len(p)))
+        base.append(np.broadcast_to(b, (len(p), 3)))
+    pts, inst, vert, base = (np.concatenate(a) for a in (pts, inst, vert, base))
+    keep = np.all((pts >= 0) & (pts < np.array([edge, edge, height])), axis=1)
+    pts, inst, vert, base = pts[keep], inst[keep], vert[keep], base[keep]
+    n_raw = len(pts)
+    c = np.floor(pts / voxel).astype(np.int64)
+    key = (c[:, 0] << 40) | (c[:, 1] << 20) | c[:, 2]
+    _, first = np.unique(key, return_index=True)
+    first.sort()
+    pts, inst, vert, base = pts[first], inst[first], vert[first], base[first]
+    pts = np.round(pts, 2)
+    centre = np.array([edge / 2, edge / 2, 0.0])
+    return dict(coords=(pts - centre).astype(np.float32), feat=vert.astype(np.float32), inst=inst,
+                base=(base - centre).astype(np.float32), n_raw=n_raw, centre=centre.astype(np.float32))
+
+
+def make_batch(tiles, inner_edge=8.0):
+    """Collate tiles (list of synth_forest dicts) into the model's input dict."""
+    coords, feats, bids, sem, inst, off, mi, mo, ms, cen = [], [], [], [], [], [], [], [], [], []
+    for b, t in enumerate(tiles):
+        n = len(t['coords'])
+        xyz = torch.from_numpy(t['coords'])
+        tree = torch.from_numpy(t['inst'] > 0)
+        inner = (xyz[:, 0].abs() < inner_edge / 2) & (xyz[:, 1].abs() < inner_edge / 2)
+        o = torch.from_numpy(t['base']) - xyz
+        o[~tree] = 0
+        coords.append(xyz)
+        feats.append(torch.from_numpy(t['feat']).reshape(-1, 1))
+        bids.append(torch.full((n,), b, dtype=torch.long))
+        sem.append(torch.where(tree, TREE_CLASS, NON_TREE_CLASS).long())
+        inst.append(torch.from_numpy(t['inst']).long())
+        off.append(o.float())
+        mi.append(inner)
+        ms.append(inner.clone())
+        mo.append(inner & tree)
+        cen.append(torch.from_numpy(t['centre']).reshape(1, 3).expand(n, 3))
+    return {'coords': torch.cat(coords).float(), 'input_feats': torch.cat(feats).float(),
+            'batch_ids': torch.cat(bids), 'semantic_labels': torch.cat(sem), 'instance_labels': torch.cat(inst),
+            'masks_inner': torch.cat(mi), 'masks_off': torch.cat(mo), 'masks_sem': torch.cat(ms),
+            'offset_labels': torch.cat(off), 'batch_size': len(tiles), 'centers': torch.cat(cen).float()}
+
+
+# named workloads (BASELINE.json configs; sizes per SURVEY §8d)
+WORKLOADS = {
+    'cfg1_200k': dict(edge=20.0, n_trees=20, seed=0),
+    'cfg2_2M': dict(edge=60.0, n_trees=225, seed=1),
+    'tiny': dict(edge=6.0, n_trees=2, seed=3, ground_density=300.0),
+    'small': dict(edge=10.0, n_trees=5, seed=4),
+}
+
+
+def workload(name):
+    return synth_forest(**WORKLOADS[name])
