@@ -1,0 +1,142 @@
+/* treelearn_b200 -- C ABI of the B200-native (sm_100a) TreeLearn per-tile hot path.
+ *
+ * The reference (ecker-lab/TreeLearn) has no C ABI: its hot path is reached through the Python
+ * module boundary `tree_learn.model.TreeLearn` and the un-vendored `spconv` operator library.
+ * Each entry point below names the reference interface (file:line under /root/reference) it
+ * replaces.  Conventions: plain device pointers + sizes, caller (torch) owns every buffer,
+ * `stream` is a cudaStream_t passed as void*, return 0 = ok / negative = error (text via
+ * tl_last_error()).  No hidden allocation: scratch comes from caller workspaces whose size is
+ * returned by the matching *_workspace_bytes query.  Thread-safe per stream.
+ */
+#ifndef TREELEARN_B200_H
+#define TREELEARN_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TL_OK 0
+#define TL_ERR_ARG (-1)
+#define TL_ERR_CUDA (-2)
+#define TL_ERR_REACH_ZERO (-3) /* spconv "reach zero!!!" (tree_learn/util/pipeline.py:91-97) */
+#define TL_ERR_UNSUPPORTED (-4)
+
+#define TL_MAX_SEG 3
+#define TL_TILE_ROWS 128 /* rows per rulebook tile (tile masks, padding of index tables) */
+
+const char* tl_last_error(void);
+int tl_version(void);
+/* number of kernels this library launched since the last tl_reset_launch_count() (bench `gpu_launches`) */
+long long tl_launch_count(void);
+void tl_reset_launch_count(void);
+
+/* ---- point -> voxel (replaces spconv PointToVoxel.generate_voxel_with_id + the mean-pool in
+ *      tree_learn/model/tree_learn.py:129-167).  Voxels come out Morton-sorted per batch element.
+ * coords [N,3] f32, feats [N,F] f32 (may be NULL when F==0), batch_ids [N] i64 ascending.
+ * out: voxel_keys [<=N] u64, voxel_coords [<=N,4] i32 (b,x,y,z), voxel_feats [<=N,F+3] f32 in
+ * channel order [feat..., x,y,z], v2p [N] i64, *num_voxels (host).  Synchronises `stream` once. */
+size_t tl_voxelize_workspace_bytes(int64_t n_points);
+int tl_voxelize(const float* coords, const float* feats, int32_t n_feat, const int64_t* batch_ids,
+                int64_t n_points, int32_t batch_size, float voxel_size, int32_t use_coords, int32_t use_feats,
+                int32_t max_points_per_voxel, uint64_t* voxel_keys, int32_t* voxel_coords, float* voxel_feats,
+                int64_t* v2p, int64_t* num_voxels, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- strided (k=2,s=2) level map: replaces spconv generate_conv_inds for SparseConv3d(k2,s2) and
+ *      its reuse by SparseInverseConv3d (tree_learn/model/blocks.py:104-110,118-123).
+ * fine_keys [n_fine] sorted -> coarse_keys [<=n_fine], coarse_coords [<=n_fine,4],
+ * down_index [8][n_coarse_pad]: fine row feeding coarse row q with kappa k, or -1   (n_coarse_pad = pad128(n_fine)),
+ * up_index   [8][n_fine_pad]  : coarse row feeding fine row p if kappa(p)==k, else -1,
+ * down_mask [n_coarse_pad/128], up_mask [n_fine_pad/128]: per-tile bitmask of offsets in use.
+ * fine_shape[3] -> coarse_shape[3] = floor((S-2)/2)+1; TL_ERR_REACH_ZERO if an axis collapses.
+ * *n_coarse (host).  Synchronises `stream` once. */
+size_t tl_level_workspace_bytes(int64_t n_fine);
+int tl_build_level(const uint64_t* fine_keys, int64_t n_fine, const int32_t* fine_shape, uint64_t* coarse_keys,
+                   int32_t* coarse_coords, int32_t* down_index, uint32_t* down_mask, int32_t* up_index,
+                   uint32_t* up_mask, int32_t* coarse_shape, int64_t* n_coarse, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
+/* ---- submanifold 3^3 rulebook: replaces spconv generate_subm_conv_inds (first SubMConv3d per
+ *      indice_key: tree_learn/model/tree_learn.py:37-39, blocks.py:57-63).
+ * keys [n] sorted unique -> nbr [27][pad128(n)] i32 (row of voxel at p+delta_k or -1; k = (dx+1)*9+(dy+1)*3+(dz+1)),
+ * tile_mask [pad128(n)/128].  hash workspace: tl_rulebook_workspace_bytes(n). */
+size_t tl_rulebook_workspace_bytes(int64_t n);
+int tl_subm_rulebook(const uint64_t* keys, int64_t n, const int32_t* spatial_shape, int32_t* nbr,
+                     uint32_t* tile_mask, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- sparse convolution as a segmented gather-GEMM: replaces spconv implicit-GEMM forward for
+ *      SubMConv3d / SparseConv3d / SparseInverseConv3d and the 1x1 torch.mm of Custom1x1Subm3d
+ *      (tree_learn/model/blocks.py:29-39,57-70,104-123), with BatchNorm(eval)+ReLU, residual add
+ *      and skip-concat fused (blocks.py:72-79,140-147; tree_learn.py:42,93).
+ *   acc[r,:] = sum_seg sum_k W_seg[k] . src_seg[index_seg[k][r], :]     (index NULL => identity, n_off==1)
+ *   v = acc + residual[r,:]
+ *   out_raw = v ; out_act1 = relu(scale1*v+shift1) ; out_act2 = relu(scale2*v+shift2)   (each optional)
+ * weight layout: mode 0 (fp32 SIMT) [n_off][c_in][c_out]; mode 1 (tf32 tcgen05) [n_off][c_out][c_in]. */
+typedef struct {
+    const float* src;
+    int64_t src_stride; /* floats per row */
+    int32_t c_in;
+    int32_t n_off;
+    const int32_t* index; /* [n_off][index_stride] or NULL */
+    int64_t index_stride;
+    const uint32_t* tile_mask; /* per 128-row tile, bit k = offset k has >=1 pair; NULL = all */
+    const float* weight;
+} tl_conv_seg;
+
+typedef struct {
+    int32_t n_out;
+    int32_t c_out;
+    int32_t n_seg;
+    int32_t reserved;
+    tl_conv_seg seg[TL_MAX_SEG];
+    const float* residual; /* [n_out, c_out] or NULL */
+    float* out_raw;
+    float* out_act1;
+    const float* scale1;
+    const float* shift1;
+    float* out_act2;
+    const float* scale2;
+    const float* shift2;
+} tl_conv_desc;
+
+#define TL_MODE_FP32 0
+#define TL_MODE_TF32 1
+int tl_conv_fwd(const tl_conv_desc* desc, int32_t mode, void* stream);
+
+/* ---- voxel -> point gather + the two MLP heads: replaces `features[v2p_map]` and MLP forward
+ *      (tree_learn/model/tree_learn.py:97-103, blocks.py:8-18).  BN(eval) is folded into w1/b1 by the host.
+ * voxel_feats [M,C]; v2p [N]; per head h in {sem(2), off(3)}: w1 [C][C] (row = out), b1 [C], w2 [O][C], b2 [O]. */
+int tl_heads_fwd(const float* voxel_feats, const int64_t* v2p, int64_t n_points, int32_t channels,
+                 const float* sem_w1, const float* sem_b1, const float* sem_w2, const float* sem_b2,
+                 const float* off_w1, const float* off_b1, const float* off_w2, const float* off_b2,
+                 float* backbone_feats, float* sem_logits, float* offsets, void* stream);
+
+/* ---- overlap merge: replaces `ensemble` (tree_learn/util/pipeline.py:113-141): group rows by
+ *      round(coords,2) and average `n_val` float columns; output sorted by (x,y,z).
+ * values [n, n_val] f32 -> out_coords [<=n,3], out_values [<=n,n_val], *n_groups (host). */
+size_t tl_merge_workspace_bytes(int64_t n);
+int tl_merge_groupby_mean(const float* coords, const float* values, int64_t n, int32_t n_val, float* out_coords,
+                          float* out_values, int32_t* group_of_row, int64_t* n_groups, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
+/* ---- DBSCAN(eps, min_samples=2)-equivalent clustering + size filter + consecutive relabel:
+ *      replaces `group_dbscan` (tree_learn/util/pipeline.py:173-180, 195-206).
+ * points [n,2] f32 -> labels [n] i64: start_num.. for clusters with >= min_cluster_size points
+ * (numbered by lowest member index), else not_assigned.  *n_clusters (host). */
+size_t tl_cluster_workspace_bytes(int64_t n);
+int tl_cluster_radius_cc(const float* points_xy, int64_t n, double radius, int64_t min_cluster_size,
+                         int64_t not_assigned_label, int64_t start_num, int64_t* labels, int64_t* n_clusters,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- kNN(k) majority vote: replaces `assign_remaining_points_nearest_neighbor`
+ *      (tree_learn/util/pipeline.py:287-296).  ref [nr,3] f32 + ref_labels [nr] i64; query [nq,3] ->
+ * out_labels [nq] (most frequent label among the k nearest, ties -> smallest label). */
+size_t tl_knn_workspace_bytes(int64_t n_ref, int64_t n_query);
+int tl_knn_vote(const float* ref_xyz, const int64_t* ref_labels, int64_t n_ref, const float* query_xyz,
+                int64_t n_query, int32_t k, int64_t* out_labels, void* workspace, size_t workspace_bytes,
+                void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,247 @@
+"""GPU parity tests (run on the B200 box): every CUDA op called through the C-ABI against the oracle on the
+same seeded inputs.  Integer / index work must be bit-exact; floating point within the stated tolerance."""
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cluster_ref, model_ref, spconv_ref as sp
+from treelearn_b200 import TreeLearn, pipeline, sparse, synth, _lib
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+FP32_TOL = dict(atol=2e-4, rtol=1e-4)     # fp32 SIMT path: only summation order differs from the oracle
+
+
+def _tile(name='tiny'):
+    return synth.make_batch([synth.workload(name)])
+
+
+def _key_rows(idx):
+    """Map (b,x,y,z) rows -> dict for order-free comparison."""
+    return {tuple(r): i for i, r in enumerate(np.asarray(idx).tolist())}
+
+
+def _voxelize_both(batch, use_feats=True):
+    dev = 'cuda'
+    vf, vc, keys, v2p = sparse.voxelize(batch['coords'].to(dev), batch['input_feats'].to(dev),
+                                        batch['batch_ids'].to(dev), batch['batch_size'], 0.1, False, use_feats, 3)
+    ovf, ovi, ov2p, oshape = model_ref.voxelize_ref(batch['coords'], batch['input_feats'], batch['batch_ids'],
+                                                    batch['batch_size'], 0.1, False, use_feats, 3)
+    return (vf, vc, keys, v2p), (ovf, ovi, ov2p, oshape)
+
+
+def test_voxelize_bit_exact_partition_and_mean():
+    tiles = [synth.synth_forest(edge=5.0, n_trees=2, seed=s, ground_density=200.0) for s in (1, 2)]
+    # un-rounded duplicates so that voxels hold several points (mean-pool of the first <=3 is exercised)
+    for t in tiles:
+        t['coords'] = np.concatenate([t['coords'], t['coords'][::3] + np.float32(0.013)])
+        t['feat'] = np.concatenate([t['feat'], t['feat'][::3] * np.float32(0.5)])
+        t['inst'] = np.concatenate([t['inst'], t['inst'][::3]])
+        t['base'] = np.concatenate([t['base'], t['base'][::3]])
+    batch = synth.make_batch(tiles)
+    (vf, vc, keys, v2p), (ovf, ovi, ov2p, _) = _voxelize_both(batch)
+    vc, v2p, vf = vc.cpu().numpy(), v2p.cpu().numpy(), vf.cpu().numpy()
+    assert len(vc) == len(ovi)
+    assert np.all(np.diff(keys.cpu().numpy()) > 0), 'voxel keys must be strictly ascending (Morton order)'
+    mine, theirs = _key_rows(vc), _key_rows(ovi.numpy())
+    assert set(mine) == set(theirs)                                   # same voxel set, bit exact
+    # same point -> voxel partition: compare the voxel coordinates each point lands in
+    assert np.array_equal(vc[v2p], ovi.numpy()[ov2p.numpy()])
+    perm = np.array([theirs[tuple(r)] for r in vc.tolist()])
+    assert np.array_equal(vf, ovf.numpy()[perm]), 'mean-pooled features must be bit exact'
+
+
+def test_rulebooks_bit_exact():
+    batch = synth.make_batch([synth.synth_forest(edge=5.0, n_trees=2, seed=5, ground_density=200.0),
+                              synth.synth_forest(edge=4.0, n_trees=1, seed=6, ground_density=200.0)])
+    (vf, vc, keys, v2p), _ = _voxelize_both(batch)
+    shape = [40, 41, 130]     # deliberately tight and odd so the bounds rule and the odd-edge rule both bite
+    levels = sparse.build_levels(keys, vc, shape, 4)
+    idx = vc.cpu().numpy()
+    for l, lv in enumerate(levels):
+        coords = lv.coords.cpu().numpy()
+        n = lv.n
+        assert n == len(coords)
+        ref_nbr = sp.subm_neighbour_table(coords, lv.shape, 3)          # rows in MY order => directly comparable
+        mine = lv.nbr.cpu().numpy()[:, :n].astype(np.int64)
+        # voxels outside spatial_shape: spconv semantics undefined; this library keeps the centre tap only
+        inside = np.all(coords[:, 1:] < np.asarray(lv.shape)[None, :], axis=1)
+        assert np.array_equal(mine[:, inside], ref_nbr[:, inside]), f'subm rulebook level {l}'
+        assert np.all(lv.nbr.cpu().numpy()[:, n:] == -1)
+        tm = lv.nbr_mask.cpu().numpy().astype(np.uint32)
+        for t in range(len(tm)):
+            rows = mine[:, t * 128:(t + 1) * 128]
+            expect = sum(1 << k for k in range(27) if (rows[k] >= 0).any())
+            assert int(tm[t]) == expect
+        if l + 1 < len(levels):
+            out_idx, out_shape, in_row, kappa, out_row = sp.strided_pairs(coords, lv.shape)
+            nxt = levels[l + 1]
+            assert nxt.shape == out_shape and nxt.n == len(out_idx)
+            assert np.array_equal(nxt.coords.cpu().numpy(), out_idx), 'coarse voxels: sorted unique, same order'
+            down = lv.down_index.cpu().numpy()
+            up = lv.up_index.cpu().numpy()
+            exp_down = -np.ones_like(down)
+            exp_up = -np.ones_like(up)
+            exp_down[kappa, out_row] = in_row
+            exp_up[kappa, in_row] = out_row
+            assert np.array_equal(down, exp_down) and np.array_equal(up, exp_up)
+
+
+def test_reach_zero_error_contract():
+    batch = _tile()
+    (vf, vc, keys, v2p), _ = _voxelize_both(batch)
+    with pytest.raises(ValueError, match='reach zero!!!'):
+        sparse.build_levels(keys, vc, [70, 70, 210], 8)
+
+
+@pytest.mark.parametrize('ci,co', [(4, 32), (32, 32), (64, 32), (96, 96), (224, 224), (8, 24)])
+def test_subm_conv_layer_parity(ci, co):
+    batch = synth.make_batch([synth.synth_forest(edge=4.0, n_trees=2, seed=9, ground_density=150.0)])
+    (vf, vc, keys, v2p), _ = _voxelize_both(batch)
+    lv = sparse.build_levels(keys, vc, [500, 500, 1000], 1)[0]
+    g = torch.Generator().manual_seed(ci * 1000 + co)
+    x = torch.randn((lv.n, ci), generator=g)
+    w = torch.randn((co, 3, 3, 3, ci), generator=g) / (27 * ci) ** 0.5
+    res = torch.randn((lv.n, co), generator=g)
+    s, t = torch.rand(co, generator=g) + 0.5, torch.randn(co, generator=g)
+    ref = model_ref._subm(x, sp.subm_neighbour_table(vc.cpu().numpy(), [500, 500, 1000]), w) + res
+    wp = w.reshape(co, 27, ci).permute(1, 2, 0).contiguous().cuda()
+    raw, act = sparse.conv([sparse.Seg(x.cuda(), wp, lv.nbr, lv.nbr_mask)], lv.n, co, _lib.MODE_FP32,
+                           residual=res.cuda(), raw=True, act1=(s.cuda(), t.cuda()))
+    assert torch.allclose(raw.cpu(), ref, **FP32_TOL)
+    assert torch.allclose(act.cpu(), torch.relu(ref * s + t), **FP32_TOL)
+
+
+def test_strided_and_inverse_conv_parity():
+    batch = synth.make_batch([synth.synth_forest(edge=4.0, n_trees=2, seed=10, ground_density=150.0)])
+    (vf, vc, keys, v2p), _ = _voxelize_both(batch)
+    lv, nx = sparse.build_levels(keys, vc, [500, 500, 1000], 2)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn((lv.n, 32), generator=g)
+    wd = torch.randn((64, 2, 2, 2, 32), generator=g) / 16
+    wu = torch.randn((32, 2, 2, 2, 64), generator=g) / 16
+    out_idx, out_shape, in_row, kappa, out_row = sp.strided_pairs(vc.cpu().numpy(), [500, 500, 1000])
+    ref_d = model_ref._pairs_conv(x, wd, in_row, kappa, out_row, len(out_idx))
+    ref_u = model_ref._pairs_conv(ref_d, wu, out_row, kappa, in_row, lv.n)
+    d = sparse.conv([sparse.Seg(x.cuda(), wd.reshape(64, 8, 32).permute(1, 2, 0).contiguous().cuda(), lv.down_index,
+                                lv.down_mask)], nx.n, 64, _lib.MODE_FP32, raw=True)
+    u = sparse.conv([sparse.Seg(d, wu.reshape(32, 8, 64).permute(1, 2, 0).contiguous().cuda(), lv.up_index,
+                                lv.up_mask)], lv.n, 32, _lib.MODE_FP32, raw=True)
+    assert torch.allclose(d.cpu(), ref_d, **FP32_TOL)
+    assert torch.allclose(u.cpu(), ref_u, **FP32_TOL)
+
+
+def _load_model_fixture():
+    g = np.load(os.path.join(GOLD, 'model_small.npz'))
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith('sd:')}
+    batch = {k[6:]: torch.from_numpy(g[k]) for k in g.files if k.startswith('batch:')}
+    batch['batch_size'] = int(batch['batch_size'])
+    out = {k[4:]: torch.from_numpy(g[k]) for k in g.files if k.startswith('out:')}
+    return g, sd, batch, out
+
+
+def test_model_matches_reference_code_golden():
+    """Golden vectors produced by the reference's own model code (tests/golden/make_golden.py)."""
+    g, sd, batch, out = _load_model_fixture()
+    net = TreeLearn(channels=8, num_blocks=3, use_feats=True, use_coords=False, spatial_shape=[500, 500, 1000])
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda().eval()
+    with torch.no_grad():
+        mine = net(batch, return_loss=False)
+        loss, ld = net(batch, return_loss=True)
+    for k, v in out.items():
+        assert mine[k].is_cuda
+        assert torch.allclose(mine[k].cpu(), v, **FP32_TOL), k
+    assert abs(loss.item() - float(g['loss'])) < 1e-3
+    assert abs(ld['semantic_loss'].item() - float(g['semantic_loss'])) < 1e-3
+    assert abs(ld['offset_loss'].item() - float(g['offset_loss'])) < 1e-3
+
+
+def test_default_model_vs_oracle_offsets_within_1e3():
+    """Default 7-level / 32-channel network on a synthetic tile: per-point offsets within 1e-3 (north_star)."""
+    batch = _tile('tiny')
+    sd = model_ref.make_state_dict(channels=32, num_blocks=7, seed=0)
+    net = TreeLearn(use_feats=False, use_coords=False, spatial_shape=[500, 500, 1000])
+    net.load_state_dict(sd)
+    net = net.cuda().eval()
+    with torch.no_grad():
+        mine = net(batch, return_loss=False)
+        ref = model_ref.forward_ref(sd, batch, spatial_shape=[500, 500, 1000])
+    assert (mine['offset_predictions'].cpu() - ref['offset_predictions']).abs().max() < 1e-3
+    assert (mine['semantic_prediction_logits'].cpu() - ref['semantic_prediction_logits']).abs().max() < 1e-3
+    assert torch.allclose(mine['backbone_feats'].cpu(), ref['backbone_feats'], atol=1e-3, rtol=1e-3)
+
+
+def test_spatial_shape_none_and_batch_of_two():
+    tiles = [synth.synth_forest(edge=4.0, n_trees=1, seed=s, ground_density=120.0) for s in (31, 32)]
+    batch = synth.make_batch(tiles)
+    sd = model_ref.make_state_dict(channels=8, num_blocks=3, seed=2)
+    net = TreeLearn(channels=8, num_blocks=3, use_feats=True, use_coords=True, spatial_shape=None)
+    net.load_state_dict(sd)
+    net = net.cuda().eval()
+    with torch.no_grad():
+        mine = net(batch, return_loss=False)
+        ref = model_ref.forward_ref(sd, batch, use_coords=True, use_feats=True, spatial_shape=None)
+    for k in ref:
+        assert torch.allclose(mine[k].cpu(), ref[k], atol=5e-4, rtol=1e-3), k
+
+
+# ---- merge / clustering / kNN --------------------------------------------------------------------
+def _cluster_fixture():
+    return np.load(os.path.join(GOLD, 'cluster_small.npz'))
+
+
+NAMES = ['coords', 'semantic_scores', 'semantic_labels', 'offset_predictions', 'offset_labels', 'instance_labels',
+         'feats', 'input_feats']
+
+
+def test_ensemble_matches_reference_golden():
+    g = _cluster_fixture()
+    out = pipeline.ensemble(**{n: g['ens_in:' + n] for n in NAMES})
+    for n, a in zip(NAMES, out):
+        ref = g['ens_out:' + n]
+        assert a.dtype == ref.dtype and a.shape == ref.shape, n
+        if a.dtype == np.int64:
+            assert np.array_equal(a, ref), n
+        else:
+            assert np.allclose(a, ref, rtol=1e-5, atol=1e-6), n
+    assert np.array_equal(out[0], g['ens_out:coords']), 'merged coordinates and their order are bit exact'
+
+
+def test_get_instances_and_knn_match_reference_golden():
+    g = _cluster_fixture()
+    cfg = SimpleNamespace(tree_conf_thresh=0.5, tau_vert=0.6, tau_off=4, tau_group=0.15, tau_min=50, use_hdbscan=False)
+    coords, logits, offs, vert = g['ens_out:coords'], g['ens_out:semantic_scores'], g['ens_out:offset_predictions'], \
+        g['ens_out:input_feats'][:, -1]
+    inst = pipeline.get_instances(coords, offs, logits, cfg, vert, 0, 0, -1, 1)
+    assert inst.dtype == np.int64 and np.array_equal(inst, g['instances'])
+    tm = inst != 0
+    assigned = pipeline.assign_remaining_points_nearest_neighbor(coords[tm] + offs[tm], inst[tm], -1)
+    assert np.array_equal(assigned, g['assigned'])
+    cfg.use_hdbscan = True
+    with pytest.raises(NotImplementedError):
+        pipeline.get_instances(coords, offs, logits, cfg, vert, 0, 0, -1, 1)
+
+
+def test_group_dbscan_label_ids_match_sklearn_golden():
+    g = _cluster_fixture()
+    assert np.array_equal(pipeline.group_dbscan(g['p2'], 0.15, 20, -1, 1), g['p2_group'])
+    raw = pipeline.group_dbscan(g['p2'], 0.15, 0, -1, 0)          # no size filter: raw DBSCAN numbering
+    assert np.array_equal(raw, g['p2_raw'])
+
+
+@pytest.mark.parametrize('n,seed', [(1, 0), (2, 1), (777, 2), (20000, 3)])
+def test_cluster_and_knn_vs_oracle_random(n, seed):
+    rng = np.random.default_rng(seed)
+    pts = (rng.normal(size=(n, 2)) * 0.6).astype(np.float32)
+    pts[: n // 3] = np.round(pts[: n // 3], 1)                   # exact duplicates and exact-distance ties
+    assert np.array_equal(pipeline.group_dbscan(pts, 0.15, 3, -1, 1), cluster_ref.group_dbscan_ref(pts, 0.15, 3, -1, 1))
+    if n >= 100:
+        xyz = (rng.normal(size=(n, 3)) * np.array([2.0, 2.0, 6.0])).astype(np.float32)
+        pred = rng.integers(0, 6, n) - 1
+        pred[:5] = np.arange(5)
+        assert np.array_equal(pipeline.assign_remaining_points_nearest_neighbor(xyz, pred, -1),
+                              cluster_ref.assign_remaining_ref(xyz, pred, -1))

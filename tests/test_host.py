@@ -1,0 +1,58 @@
+"""CPU tests of the host side: C-ABI library loads and exports every declared symbol, the model keeps the
+reference's state_dict layout, the product refuses to run without CUDA (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from treelearn_b200 import TreeLearn, _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, 'include', 'treelearn_b200.h')).read()
+    declared = set(re.findall(r'\b(tl_[a-z0-9_]+)\s*\(', header))
+    assert declared, 'no declarations found'
+    assert os.path.exists(_lib.LIB_PATH), 'build the extension first (python __graft_entry__.py)'
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f'{name} declared in include/treelearn_b200.h but not exported'
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert lib.tl_version() >= 1
+
+
+def test_state_dict_layout_matches_reference():
+    g = np.load(os.path.join(ROOT, 'tests', 'golden', 'model_small.npz'))
+    keys = [k[3:] for k in g.files if k.startswith('sd:')]
+    net = TreeLearn(channels=8, num_blocks=3)
+    sd = net.state_dict()
+    assert list(sd.keys()) == keys
+    for k in keys:
+        assert tuple(sd[k].shape) == g['sd:' + k].shape, k
+    net.load_state_dict({k: torch.from_numpy(g['sd:' + k]) for k in keys}, strict=True)
+    full = TreeLearn()
+    n_backbone = sum(p.numel() for n, p in full.named_parameters() if not n.startswith(('semantic_', 'offset_')))
+    assert n_backbone == 30104576
+    assert full.state_dict()['input_conv.0.weight'].shape == (32, 3, 3, 3, 4)
+
+
+def test_fixed_modules_keep_bn_in_eval():
+    net = TreeLearn(channels=8, num_blocks=2, fixed_modules=['unet'])
+    net.train()
+    assert not net.unet.blocks.block0.conv_branch._modules['0'].training
+    assert net.semantic_linear[1].training
+    assert all(not p.requires_grad for p in net.unet.parameters())
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason='checks the no-GPU failure mode')
+def test_no_cpu_fallback():
+    net = TreeLearn(channels=8, num_blocks=2).eval()
+    batch = {'coords': torch.rand(10, 3), 'input_feats': torch.rand(10, 1), 'batch_ids': torch.zeros(10, dtype=torch.long),
+             'batch_size': 1}
+    with pytest.raises(Exception):
+        with torch.no_grad():
+            net(batch, return_loss=False)

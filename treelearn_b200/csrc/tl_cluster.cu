@@ -1,0 +1,447 @@
+// Overlap merge, DBSCAN-equivalent clustering and kNN vote.
+// Integer results (group structure, partition, label ids, votes) are bit-exact against
+// oracle/cluster_ref.py, which is pinned to the reference's pandas / sklearn code.
+// Distances are evaluated in fp64 on the float32 inputs without FMA contraction, the way
+// sklearn's KD-tree evaluates its reduced distance (sum of squares in axis order).
+#include <cub/cub.cuh>
+
+#include "tl_common.cuh"
+
+namespace tl {
+
+// ------------------------------------------------------------------------------------------------
+// overlap merge: group-by round(coords, 2), mean of the value columns, sorted by (x,y,z)
+// ------------------------------------------------------------------------------------------------
+constexpr int kAxisBits = 21;
+constexpr int64_t kAxisBias = 1 << (kAxisBits - 1);
+
+__global__ void k_merge_keys(const float* __restrict__ coords, int64_t n, uint64_t* __restrict__ keys,
+                             int* __restrict__ idx) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t key = 0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        // pandas round(2) on a float32 column == rint(x * 100) / 100 evaluated in float32
+        int64_t q = (int64_t)rintf(__fmul_rn(coords[i * 3 + a], 100.0f)) + kAxisBias;
+        q = q < 0 ? 0 : (q >= (1 << kAxisBits) ? (1 << kAxisBits) - 1 : q);
+        key = (key << kAxisBits) | (uint64_t)q;
+    }
+    keys[i] = key;
+    idx[i] = (int)i;
+}
+
+__global__ void k_heads_u64(const uint64_t* __restrict__ keys, int64_t n, int* __restrict__ flag) {
+    int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    flag[j] = (j == 0 || keys[j] != keys[j - 1]) ? 1 : 0;
+}
+
+// seg_start[g] = first sorted position of group g; seg_start[n_groups] = n
+__global__ void k_segment_starts(const int* __restrict__ flag, const int* __restrict__ scan, int64_t n,
+                                 int* __restrict__ seg_start) {
+    int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    if (flag[j]) seg_start[scan[j] - 1] = (int)j;
+    if (j == n - 1) seg_start[scan[j]] = (int)n;
+}
+
+__global__ void k_merge_emit(const uint64_t* __restrict__ skeys, const int* __restrict__ sidx,
+                             const int* __restrict__ scan, const int* __restrict__ seg_start, int64_t n, int n_val,
+                             const float* __restrict__ values, float* __restrict__ out_coords,
+                             float* __restrict__ out_values, int* __restrict__ group_of_row, int n_groups) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t < n) group_of_row[sidx[t]] = scan[t] - 1;
+    const int64_t total = (int64_t)n_groups * (n_val + 3);
+    for (int64_t e = t; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int g = (int)(e / (n_val + 3)), col = (int)(e % (n_val + 3));
+        const int s = seg_start[g], end = seg_start[g + 1];
+        if (col < 3) {
+            const uint64_t key = skeys[s];
+            const int64_t q = (int64_t)((key >> (kAxisBits * (2 - col))) & ((1u << kAxisBits) - 1)) - kAxisBias;
+            out_coords[(int64_t)g * 3 + col] = __fdiv_rn((float)q, 100.0f);
+        } else {
+            double acc = 0.0;
+            for (int j = s; j < end; ++j) acc += (double)values[(int64_t)sidx[j] * n_val + (col - 3)];
+            out_values[(int64_t)g * n_val + (col - 3)] = (float)(acc / (double)(end - s));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// uniform-grid cell index shared by the clustering and kNN kernels
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t cell_key3(int64_t cx, int64_t cy, int64_t cz) {
+    return ((uint64_t)(cx + kAxisBias) << (2 * kAxisBits)) | ((uint64_t)(cy + kAxisBias) << kAxisBits) |
+           (uint64_t)(cz + kAxisBias);
+}
+
+template <int DIM>
+__global__ void k_cell_keys(const float* __restrict__ pts, int64_t n, double inv_cell, uint64_t* __restrict__ keys,
+                            int* __restrict__ idx) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int64_t c[3] = {0, 0, 0};
+#pragma unroll
+    for (int a = 0; a < DIM; ++a) {
+        int64_t v = (int64_t)floor((double)pts[i * DIM + a] * inv_cell);
+        c[a] = v < -kAxisBias + 2 ? -kAxisBias + 2 : (v > kAxisBias - 3 ? kAxisBias - 3 : v);
+    }
+    keys[i] = cell_key3(c[0], c[1], c[2]);
+    idx[i] = (int)i;
+}
+
+template <int DIM>
+__global__ void k_cell_table(const uint64_t* __restrict__ skeys, const int* __restrict__ sidx,
+                             const int* __restrict__ flag, const int* __restrict__ scan, int64_t n,
+                             const float* __restrict__ pts, float* __restrict__ spts, uint64_t* tkeys, int* tvals,
+                             uint64_t mask) {
+    int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const int i = sidx[j];
+#pragma unroll
+    for (int a = 0; a < DIM; ++a) spts[j * DIM + a] = pts[(int64_t)i * DIM + a];
+    if (flag[j]) hash_insert(tkeys, tvals, mask, skeys[j], scan[j] - 1);
+}
+
+struct CellGrid {
+    uint64_t *keys_in, *keys_out, *tkeys;
+    int *idx_in, *idx_out, *flag, *scan, *seg_start, *tvals;
+    float* spts;
+    uint64_t cap;
+    void* cub_tmp;
+    size_t cub_bytes;
+};
+
+static size_t cub_sort_scan_bytes(int64_t n) {
+    size_t a = 0, b = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, a, (uint64_t*)nullptr, (uint64_t*)nullptr, (int*)nullptr, (int*)nullptr,
+                                    (int)n);
+    cub::DeviceScan::InclusiveSum(nullptr, b, (int*)nullptr, (int*)nullptr, (int)n);
+    return align_up(a > b ? a : b);
+}
+
+static size_t grid_bytes(int64_t n) {
+    uint64_t cap = table_capacity(n);
+    return 2 * align_up(n * 8) + 5 * align_up((n + 1) * 4) + align_up(n * 3 * 4) + align_up(cap * 8) +
+           align_up(cap * 4) + cub_sort_scan_bytes(n) + 2048;
+}
+
+static bool carve_grid(Carver& c, int64_t n, CellGrid& g) {
+    g.keys_in = c.take<uint64_t>(n);
+    g.keys_out = c.take<uint64_t>(n);
+    g.idx_in = c.take<int>(n + 1);
+    g.idx_out = c.take<int>(n + 1);
+    g.flag = c.take<int>(n + 1);
+    g.scan = c.take<int>(n + 1);
+    g.seg_start = c.take<int>(n + 1);
+    g.spts = c.take<float>(n * 3);
+    g.cap = table_capacity(n);
+    g.tkeys = c.take<uint64_t>(g.cap);
+    g.tvals = c.take<int>(g.cap);
+    g.cub_bytes = cub_sort_scan_bytes(n);
+    g.cub_tmp = c.take<char>(g.cub_bytes);
+    return c.ok();
+}
+
+// sort points into cells, build (cell key -> segment id) table and the cell-sorted coordinate copy
+template <int DIM>
+static int build_grid(const float* pts, int64_t n, double cell, CellGrid& g, cudaStream_t stream) {
+    const int T = 256;
+    const unsigned nb = (unsigned)((n + T - 1) / T);
+    k_cell_keys<DIM><<<nb, T, 0, stream>>>(pts, n, 1.0 / cell, g.keys_in, g.idx_in);
+    TL_LAUNCH_CHECK();
+    size_t cb = g.cub_bytes;
+    TL_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(g.cub_tmp, cb, g.keys_in, g.keys_out, g.idx_in, g.idx_out, (int)n, 0,
+                                                  3 * kAxisBits, stream));
+    k_heads_u64<<<nb, T, 0, stream>>>(g.keys_out, n, g.flag);
+    TL_LAUNCH_CHECK();
+    cb = g.cub_bytes;
+    TL_CUDA_CHECK(cub::DeviceScan::InclusiveSum(g.cub_tmp, cb, g.flag, g.scan, (int)n, stream));
+    k_segment_starts<<<nb, T, 0, stream>>>(g.flag, g.scan, n, g.seg_start);
+    TL_LAUNCH_CHECK();
+    TL_CUDA_CHECK(cudaMemsetAsync(g.tkeys, 0xFF, g.cap * 8, stream));
+    k_cell_table<DIM><<<nb, T, 0, stream>>>(g.keys_out, g.idx_out, g.flag, g.scan, n, pts, g.spts, g.tkeys, g.tvals,
+                                             g.cap - 1);
+    TL_LAUNCH_CHECK();
+    return TL_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// DBSCAN(eps, min_samples=2) == connected components of the d<=eps graph (min-index union-find)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int uf_find(int* parent, int x) {
+    int p = parent[x];
+    while (p != x) {
+        int gp = parent[p];
+        if (gp != p) parent[x] = gp;  // path halving (benign race: only ever points closer to the root)
+        x = p;
+        p = gp;
+    }
+    return x;
+}
+__device__ __forceinline__ void uf_union(int* parent, int a, int b) {
+    while (true) {
+        a = uf_find(parent, a);
+        b = uf_find(parent, b);
+        if (a == b) return;
+        const int hi = a > b ? a : b, lo = a > b ? b : a;
+        if (atomicCAS(&parent[hi], hi, lo) == hi) return;  // hook the larger root under the smaller: root == min index
+    }
+}
+
+__global__ void k_iota(int* p, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) p[i] = (int)i;
+}
+
+__global__ void k_cc_link(const uint64_t* __restrict__ skeys, const int* __restrict__ sidx,
+                          const float* __restrict__ spts, const int* __restrict__ seg_start,
+                          const uint64_t* __restrict__ tkeys, const int* __restrict__ tvals, uint64_t mask, int64_t n,
+                          double r2, int* parent) {
+    int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const int i = sidx[j];
+    const double x = spts[j * 2], y = spts[j * 2 + 1];
+    const uint64_t key = skeys[j];
+    const int64_t cx = (int64_t)(key >> (2 * kAxisBits)) - kAxisBias;
+    const int64_t cy = (int64_t)((key >> kAxisBits) & ((1u << kAxisBits) - 1)) - kAxisBias;
+    for (int dx = -1; dx <= 1; ++dx)
+        for (int dy = -1; dy <= 1; ++dy) {
+            const int seg = hash_find(tkeys, tvals, mask, cell_key3(cx + dx, cy + dy, 0));
+            if (seg < 0) continue;
+            const int s = seg_start[seg], e = seg_start[seg + 1];
+            for (int j2 = s; j2 < e; ++j2) {
+                const int i2 = sidx[j2];
+                if (i2 >= i) continue;  // each unordered pair once
+                const double ddx = x - (double)spts[j2 * 2], ddy = y - (double)spts[j2 * 2 + 1];
+                const double d2 = __dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy));
+                if (d2 <= r2) uf_union(parent, i, i2);
+            }
+        }
+}
+
+__global__ void k_cc_roots(int* parent, int64_t n, int* __restrict__ root, int* __restrict__ size) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int r = uf_find(parent, (int)i);
+    root[i] = r;
+    atomicAdd(&size[r], 1);
+}
+
+__global__ void k_cc_valid(const int* __restrict__ root, const int* __restrict__ size, int64_t n, int min_size,
+                           int* __restrict__ valid) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    valid[i] = (root[i] == (int)i && size[i] >= 2 && size[i] >= min_size) ? 1 : 0;
+}
+
+__global__ void k_cc_labels(const int* __restrict__ root, const int* __restrict__ valid, const int* __restrict__ rank,
+                            int64_t n, int64_t not_assigned, int64_t start_num, int64_t* __restrict__ labels) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int r = root[i];
+    labels[i] = valid[r] ? start_num + (int64_t)(rank[r] - 1) : not_assigned;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kNN majority vote over a 3-D cell grid, expanding cube search + exact brute-force fallback
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxK = 8;
+constexpr int kMaxRing = 6;
+
+struct TopK {
+    double d[kMaxK];
+    int64_t lab[kMaxK];
+    int idx[kMaxK];
+    int k;
+    __device__ void init(int k_) {
+        k = k_;
+        for (int t = 0; t < kMaxK; ++t) d[t] = 1e300, lab[t] = 0, idx[t] = 0x7fffffff;
+    }
+    // ordered by (distance, reference index): deterministic under ties
+    __device__ void push(double dist, int64_t label, int index) {
+        if (dist > d[k - 1] || (dist == d[k - 1] && index >= idx[k - 1])) return;
+        int t = k - 1;
+        while (t > 0 && (d[t - 1] > dist || (d[t - 1] == dist && idx[t - 1] > index))) {
+            d[t] = d[t - 1], lab[t] = lab[t - 1], idx[t] = idx[t - 1];
+            --t;
+        }
+        d[t] = dist, lab[t] = label, idx[t] = index;
+    }
+    __device__ int64_t vote() const {  // most frequent label, ties -> smallest label
+        int64_t best = 0;
+        int best_cnt = 0;
+        for (int a = 0; a < k; ++a) {
+            int cnt = 0;
+            for (int b = 0; b < k; ++b) cnt += (lab[b] == lab[a]);
+            if (cnt > best_cnt || (cnt == best_cnt && lab[a] < best)) best = lab[a], best_cnt = cnt;
+        }
+        return best;
+    }
+};
+
+__global__ void k_knn_vote(const float* __restrict__ query, int64_t nq, const uint64_t* __restrict__ tkeys,
+                           const int* __restrict__ tvals, uint64_t mask, const int* __restrict__ seg_start,
+                           const int* __restrict__ sidx, const float* __restrict__ spts,
+                           const int64_t* __restrict__ ref_labels, int64_t n_ref, double cell, int k,
+                           int64_t* __restrict__ out) {
+    int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const double x = query[q * 3], y = query[q * 3 + 1], z = query[q * 3 + 2];
+    const int64_t cx = (int64_t)floor(x / cell), cy = (int64_t)floor(y / cell), cz = (int64_t)floor(z / cell);
+    TopK top;
+    bool done = false;
+    for (int ring = 1; ring <= kMaxRing && !done; ++ring) {
+        top.init(k);
+        for (int dx = -ring; dx <= ring; ++dx)
+            for (int dy = -ring; dy <= ring; ++dy)
+                for (int dz = -ring; dz <= ring; ++dz) {
+                    const int seg = hash_find(tkeys, tvals, mask, cell_key3(cx + dx, cy + dy, cz + dz));
+                    if (seg < 0) continue;
+                    for (int j = seg_start[seg]; j < seg_start[seg + 1]; ++j) {
+                        const double ax = x - (double)spts[j * 3], ay = y - (double)spts[j * 3 + 1],
+                                     az = z - (double)spts[j * 3 + 2];
+                        const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)), __dmul_rn(az, az));
+                        top.push(d2, ref_labels[sidx[j]], sidx[j]);
+                    }
+                }
+        // every reference closer than ring*cell (minus the query's offset inside its cell, bounded by 0) was seen
+        const double safe = (double)ring * cell;
+        done = top.d[k - 1] <= safe * safe;
+    }
+    if (!done) {  // sparse neighbourhood: exact scan of all references (rare)
+        top.init(k);
+        for (int64_t j = 0; j < n_ref; ++j) {
+            const double ax = x - (double)spts[j * 3], ay = y - (double)spts[j * 3 + 1], az = z - (double)spts[j * 3 + 2];
+            const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)), __dmul_rn(az, az));
+            top.push(d2, ref_labels[sidx[j]], sidx[j]);
+        }
+    }
+    out[q] = top.vote();
+}
+
+}  // namespace tl
+
+using namespace tl;
+
+extern "C" {
+
+size_t tl_merge_workspace_bytes(int64_t n) {
+    if (n <= 0) return 256;
+    return 2 * align_up(n * 8) + 5 * align_up((n + 1) * 4) + cub_sort_scan_bytes(n) + 2048;
+}
+
+int tl_merge_groupby_mean(const float* coords, const float* values, int64_t n, int32_t n_val, float* out_coords,
+                          float* out_values, int32_t* group_of_row, int64_t* n_groups, void* workspace,
+                          size_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    TL_REQUIRE(n > 0 && n < (1ll << 31), "tl_merge_groupby_mean: n=%lld out of range", (long long)n);
+    Carver c(workspace, workspace_bytes);
+    uint64_t* keys_in = c.take<uint64_t>(n);
+    uint64_t* keys_out = c.take<uint64_t>(n);
+    int* idx_in = c.take<int>(n + 1);
+    int* idx_out = c.take<int>(n + 1);
+    int* flag = c.take<int>(n + 1);
+    int* scan = c.take<int>(n + 1);
+    int* seg_start = c.take<int>(n + 1);
+    size_t cub_b = cub_sort_scan_bytes(n);
+    void* cub_tmp = c.take<char>(cub_b);
+    TL_REQUIRE(c.ok(), "tl_merge_groupby_mean: workspace too small");
+    const int T = 256;
+    const unsigned nb = (unsigned)((n + T - 1) / T);
+    k_merge_keys<<<nb, T, 0, stream>>>(coords, n, keys_in, idx_in);
+    TL_LAUNCH_CHECK();
+    size_t cb = cub_b;
+    TL_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(cub_tmp, cb, keys_in, keys_out, idx_in, idx_out, (int)n, 0,
+                                                  3 * kAxisBits, stream));
+    k_heads_u64<<<nb, T, 0, stream>>>(keys_out, n, flag);
+    TL_LAUNCH_CHECK();
+    cb = cub_b;
+    TL_CUDA_CHECK(cub::DeviceScan::InclusiveSum(cub_tmp, cb, flag, scan, (int)n, stream));
+    k_segment_starts<<<nb, T, 0, stream>>>(flag, scan, n, seg_start);
+    TL_LAUNCH_CHECK();
+    int ng = 0;
+    TL_CUDA_CHECK(cudaMemcpyAsync(&ng, scan + (n - 1), sizeof(int), cudaMemcpyDeviceToHost, stream));
+    TL_CUDA_CHECK(cudaStreamSynchronize(stream));
+    k_merge_emit<<<nb, T, 0, stream>>>(keys_out, idx_out, scan, seg_start, n, n_val, values, out_coords, out_values,
+                                       group_of_row, ng);
+    TL_LAUNCH_CHECK();
+    *n_groups = ng;
+    return TL_OK;
+}
+
+size_t tl_cluster_workspace_bytes(int64_t n) {
+    if (n <= 0) return 256;
+    return grid_bytes(n) + 5 * align_up((n + 1) * 4) + 1024;
+}
+
+int tl_cluster_radius_cc(const float* points_xy, int64_t n, double radius, int64_t min_cluster_size,
+                         int64_t not_assigned_label, int64_t start_num, int64_t* labels, int64_t* n_clusters,
+                         void* workspace, size_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    *n_clusters = 0;
+    if (n == 0) return TL_OK;
+    TL_REQUIRE(n > 0 && n < (1ll << 31) && radius > 0, "tl_cluster_radius_cc: n=%lld radius=%g", (long long)n, radius);
+    Carver c(workspace, workspace_bytes);
+    CellGrid g;
+    bool ok = carve_grid(c, n, g);
+    int* parent = c.take<int>(n + 1);
+    int* root = c.take<int>(n + 1);
+    int* size = c.take<int>(n + 1);
+    int* valid = c.take<int>(n + 1);
+    int* rank = c.take<int>(n + 1);
+    TL_REQUIRE(ok && c.ok(), "tl_cluster_radius_cc: workspace too small");
+    // cells a hair wider than the radius: two points within the radius are always in adjacent cells
+    int rc = build_grid<2>(points_xy, n, radius * (1.0 + 1e-7), g, stream);
+    if (rc != TL_OK) return rc;
+    const int T = 256;
+    const unsigned nb = (unsigned)((n + T - 1) / T);
+    k_iota<<<nb, T, 0, stream>>>(parent, n);
+    TL_LAUNCH_CHECK();
+    TL_CUDA_CHECK(cudaMemsetAsync(size, 0, sizeof(int) * n, stream));
+    k_cc_link<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(g.keys_out, g.idx_out, g.spts, g.seg_start, g.tkeys,
+                                                               g.tvals, g.cap - 1, n, radius * radius, parent);
+    TL_LAUNCH_CHECK();
+    k_cc_roots<<<nb, T, 0, stream>>>(parent, n, root, size);
+    TL_LAUNCH_CHECK();
+    const int min_size = (int)(min_cluster_size > 0x7fffffff ? 0x7fffffff : (min_cluster_size < 0 ? 0 : min_cluster_size));
+    k_cc_valid<<<nb, T, 0, stream>>>(root, size, n, min_size, valid);
+    TL_LAUNCH_CHECK();
+    size_t cb = g.cub_bytes;
+    TL_CUDA_CHECK(cub::DeviceScan::InclusiveSum(g.cub_tmp, cb, valid, rank, (int)n, stream));
+    k_cc_labels<<<nb, T, 0, stream>>>(root, valid, rank, n, not_assigned_label, start_num, labels);
+    TL_LAUNCH_CHECK();
+    int nc = 0;
+    TL_CUDA_CHECK(cudaMemcpyAsync(&nc, rank + (n - 1), sizeof(int), cudaMemcpyDeviceToHost, stream));
+    TL_CUDA_CHECK(cudaStreamSynchronize(stream));
+    *n_clusters = nc;
+    return TL_OK;
+}
+
+size_t tl_knn_workspace_bytes(int64_t n_ref, int64_t n_query) {
+    (void)n_query;
+    if (n_ref <= 0) return 256;
+    return grid_bytes(n_ref) + 1024;
+}
+
+int tl_knn_vote(const float* ref_xyz, const int64_t* ref_labels, int64_t n_ref, const float* query_xyz, int64_t n_query,
+                int32_t k, int64_t* out_labels, void* workspace, size_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n_query == 0) return TL_OK;
+    TL_REQUIRE(k >= 1 && k <= kMaxK, "tl_knn_vote: k=%d (1..%d)", k, kMaxK);
+    TL_REQUIRE(n_ref >= k && n_ref < (1ll << 31), "tl_knn_vote: n_ref=%lld must be >= k=%d", (long long)n_ref, k);
+    Carver c(workspace, workspace_bytes);
+    CellGrid g;
+    TL_REQUIRE(carve_grid(c, n_ref, g), "tl_knn_vote: workspace too small");
+    const double cell = 0.25;
+    int rc = build_grid<3>(ref_xyz, n_ref, cell, g, stream);
+    if (rc != TL_OK) return rc;
+    k_knn_vote<<<(unsigned)((n_query + 127) / 128), 128, 0, stream>>>(query_xyz, n_query, g.tkeys, g.tvals, g.cap - 1,
+                                                                      g.seg_start, g.idx_out, g.spts, ref_labels, n_ref,
+                                                                      cell, k, out_labels);
+    TL_LAUNCH_CHECK();
+    return TL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,286 @@
+"""`TreeLearn` -- drop-in for `tree_learn.model.TreeLearn` (reference tree_learn/model/tree_learn.py:11-126).
+
+Same constructor signature, `forward(batch, return_loss)` contract, output dict and `state_dict`
+key/shape layout (b), so `load_checkpoint` of a reference `.pth` works and
+tools/pipeline / tools/training can construct and call it unchanged.  What differs is what it
+runs on: no spconv module tree -- parameters live in plain containers named like the reference's
+modules, and the forward is a flat schedule of fused C-ABI kernels (treelearn_b200/csrc):
+
+    point->voxel (Morton sort) -> level pyramid + rulebooks -> ~70 segmented gather-GEMM convs,
+    each with residual add / skip-concat / 1x1 projection folded into the GEMM and the consumer's
+    BatchNorm(eval)+ReLU folded into the epilogue -> voxel->point gather + both heads.
+
+There is no CPU path: tensors are moved to the current CUDA device (like the reference's
+`cuda_cast`, tree_learn/util/train.py:28-43) and the extension must be present.
+"""
+import functools
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import _lib, sparse
+from .sparse import Seg
+
+LOSS_MULTIPLIER_SEMANTIC = 50     # reference tree_learn.py:9
+BN_EPS, BN_MOMENTUM = 1e-4, 0.1   # reference tree_learn.py:34
+
+
+class SparseConvWeight(nn.Module):
+    """Parameter holder with spconv's KRSC layout [C_out, k, k, k, C_in]; bias-free."""
+
+    def __init__(self, in_channels, out_channels, kernel_size):
+        super().__init__()
+        self.in_channels, self.out_channels, self.kernel_size = in_channels, out_channels, kernel_size
+        k = kernel_size
+        self.weight = nn.Parameter(torch.empty(out_channels, k, k, k, in_channels))
+        nn.init.kaiming_uniform_(self.weight, a=5 ** 0.5)
+
+
+class HeadMLP(nn.Sequential):
+    """Linear-BN-ReLU-Linear (reference blocks.py:8-26): keys 0.*, 1.*, 3.*."""
+
+    def __init__(self, channels, out_channels, norm_fn):
+        super().__init__(nn.Linear(channels, channels), norm_fn(channels), nn.ReLU(), nn.Linear(channels, out_channels))
+
+    def init_weights(self):
+        for m in self:
+            if isinstance(m, nn.Linear):
+                nn.init.xavier_uniform_(m.weight)
+                nn.init.constant_(m.bias, 0)
+        nn.init.normal_(self[3].weight, 0, 0.01)
+        nn.init.constant_(self[3].bias, 0)
+
+
+def _container_path(root, path):
+    """Walk/create plain nn.Module containers along a dotted path; returns (parent, leaf_name)."""
+    parts = path.split('.')
+    mod = root
+    for p in parts[:-1]:
+        if p not in mod._modules:
+            mod.add_module(p, nn.Module())
+        mod = mod._modules[p]
+    return mod, parts[-1]
+
+
+class TreeLearn(nn.Module):
+    def __init__(self, channels=32, num_blocks=7, kernel_size=3, dim_coord=3, dim_feat=1, fixed_modules=[],
+                 use_feats=True, use_coords=False, spatial_shape=None, max_num_points_per_voxel=3,
+                 voxel_size=0.1, mode='fp32', **kwargs):
+        super().__init__()
+        if kernel_size != 3:
+            raise NotImplementedError('treelearn_b200 builds the 3^3 submanifold rulebook only (reference default)')
+        self.channels, self.num_blocks = channels, num_blocks
+        self.dim_coord, self.dim_feat = dim_coord, dim_feat
+        self.voxel_size = voxel_size
+        self.fixed_modules = fixed_modules
+        self.use_feats, self.use_coords = use_feats, use_coords
+        self.spatial_shape = spatial_shape
+        self.max_num_points_per_voxel = max_num_points_per_voxel
+        self.mode = mode                      # 'fp32' (SIMT, exact-ish) or 'tf32' (tcgen05)
+        self.planes = [channels * (i + 1) for i in range(num_blocks)]
+        self._norm = functools.partial(nn.BatchNorm1d, eps=BN_EPS, momentum=BN_MOMENTUM)
+        self._packed = None
+
+        self._put('input_conv.0', SparseConvWeight(dim_coord + dim_feat, channels, 3))
+        self._declare_ublock('unet', 0)
+        self._put('output_layer.0', self._norm(channels))
+        self.semantic_linear = HeadMLP(channels, 2, self._norm)
+        self.offset_linear = HeadMLP(channels, 3, self._norm)
+        self.init_weights()
+        for name in fixed_modules:
+            for p in getattr(self, name).parameters():
+                p.requires_grad = False
+
+    # ---- parameter tree with the reference's names ------------------------------------------------
+    def _put(self, path, module):
+        parent, leaf = _container_path(self, path)
+        parent.add_module(leaf, module)
+
+    def _get(self, path):
+        mod = self
+        for p in path.split('.'):
+            mod = mod._modules[p]
+        return mod
+
+    def _declare_residual(self, p, c_in, c_out):
+        if c_in != c_out:
+            self._put(p + '.i_branch.0', SparseConvWeight(c_in, c_out, 1))
+        self._put(p + '.conv_branch.0', self._norm(c_in))
+        self._put(p + '.conv_branch.2', SparseConvWeight(c_in, c_out, 3))
+        self._put(p + '.conv_branch.3', self._norm(c_out))
+        self._put(p + '.conv_branch.5', SparseConvWeight(c_out, c_out, 3))
+
+    def _declare_ublock(self, p, l):
+        c = self.planes[l]
+        for i in range(2):
+            self._declare_residual(f'{p}.blocks.block{i}', c, c)
+        if l + 1 < self.num_blocks:
+            cn = self.planes[l + 1]
+            self._put(p + '.conv.0', self._norm(c))
+            self._put(p + '.conv.2', SparseConvWeight(c, cn, 2))
+            self._declare_ublock(p + '.u', l + 1)
+            self._put(p + '.deconv.0', self._norm(cn))
+            self._put(p + '.deconv.2', SparseConvWeight(cn, c, 2))
+            self._declare_residual(p + '.blocks_tail.block0', 2 * c, c)
+            self._declare_residual(p + '.blocks_tail.block1', c, c)
+
+    def init_weights(self):
+        for m in self.modules():
+            if isinstance(m, nn.BatchNorm1d):
+                nn.init.constant_(m.weight, 1)
+                nn.init.constant_(m.bias, 0)
+            elif isinstance(m, HeadMLP):
+                m.init_weights()
+
+    def train(self, mode=True):
+        super().train(mode)
+        for name in self.fixed_modules:      # BN of frozen modules stays in eval (reference tree_learn.py:66-72)
+            for m in getattr(self, name).modules():
+                if isinstance(m, nn.BatchNorm1d):
+                    m.eval()
+        return self
+
+    # ---- weight packing (eval): BN folded to scale/shift, conv weights to the kernel layout -------
+    def _version_key(self):
+        return (self.mode, self.input_conv._modules['0'].weight.device,
+                tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers())))
+
+    def _pack(self):
+        key = self._version_key()
+        if self._packed is not None and self._packed['key'] == key:
+            return self._packed
+        tf32 = self.mode == 'tf32'
+        pk = {'key': key}
+        with torch.no_grad():
+            for name, m in self.named_modules():
+                if isinstance(m, SparseConvWeight):
+                    w = m.weight.detach().float()
+                    co, ci = m.out_channels, m.in_channels
+                    w = w.reshape(co, -1, ci)
+                    if name.endswith(('blocks_tail.block0.conv_branch.2', 'blocks_tail.block0.i_branch.0')):
+                        # input is cat(identity, decoder) (reference blocks.py:146): one segment per half
+                        pieces = [w[:, :, :ci // 2], w[:, :, ci // 2:]]
+                    else:
+                        pieces = [w]
+                    out = []
+                    for piece in pieces:
+                        if tf32:
+                            out.append(_round_tf32(piece.permute(1, 0, 2).contiguous()))   # [K, Co, Ci]
+                        else:
+                            out.append(piece.permute(1, 2, 0).contiguous())               # [K, Ci, Co]
+                    pk[name] = out
+                elif isinstance(m, nn.BatchNorm1d) and not name.startswith(('semantic_linear', 'offset_linear')):
+                    s = (m.weight / torch.sqrt(m.running_var + m.eps)).float()
+                    t = (m.bias - m.running_mean * s).float()
+                    pk[name] = (s.contiguous(), t.contiguous())
+            for head, tag in ((self.semantic_linear, 'sem'), (self.offset_linear, 'off')):
+                bn = head[1]
+                s = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+                t = bn.bias - bn.running_mean * s
+                pk[tag + '_w1'] = (head[0].weight * s[:, None]).float().contiguous()
+                pk[tag + '_b1'] = (head[0].bias * s + t).float().contiguous()
+                pk[tag + '_w2'] = head[3].weight.float().contiguous()
+                pk[tag + '_b2'] = head[3].bias.float().contiguous()
+        self._packed = pk
+        return pk
+
+    # ---- forward ------------------------------------------------------------------------------------
+    def forward(self, batch, return_loss):
+        voxel_out, v2p = self.forward_backbone(**batch)
+        output = self.forward_head(voxel_out, v2p)
+        if return_loss:
+            output = self.get_loss(model_output=output, **batch)
+        return output
+
+    def forward_backbone(self, coords, input_feats, batch_ids, batch_size, **kwargs):
+        if self.training and torch.is_grad_enabled():
+            raise NotImplementedError('treelearn_b200: the training (batch-stat BN + backward) path is not built yet; '
+                                      'call under model.eval() / torch.no_grad()')
+        dev = torch.device('cuda', torch.cuda.current_device())
+        coords, input_feats, batch_ids = (t.to(dev, non_blocking=True) for t in (coords, input_feats, batch_ids))
+        vfeats, vcoords, keys, v2p = sparse.voxelize(
+            coords, input_feats, batch_ids, batch_size, self.voxel_size, self.use_coords, self.use_feats,
+            self.max_num_points_per_voxel)
+        if self.spatial_shape is not None:
+            shape = [int(s) for s in self.spatial_shape]
+        else:
+            shape = (vcoords[:, 1:].max(dim=0).values + 1).tolist()   # reference tree_learn.py:165
+        levels = sparse.build_levels(keys, vcoords, shape, self.num_blocks)
+        return self._run_backbone(vfeats, levels), v2p
+
+    def _run_backbone(self, vfeats, levels):
+        pk = self._pack()
+        mode = _lib.MODE_TF32 if self.mode == 'tf32' else _lib.MODE_FP32
+        g0 = levels[0]
+        x, xa = sparse.conv([Seg(vfeats, pk['input_conv.0'][0], g0.nbr, g0.nbr_mask)], g0.n, self.planes[0], mode,
+                            raw=True, act1=pk['unet.blocks.block0.conv_branch.0'])
+        return self._run_ublock('unet', 0, x, xa, levels, pk, mode, pk['output_layer.0'])
+
+    def _run_ublock(self, p, l, x, xa, levels, pk, mode, ret_act):
+        """x: raw features [n_l, C_l]; xa = relu(bn(x)) for blocks.block0; returns relu(ret_bn(level output))."""
+        g, c, n = levels[l], self.planes[l], levels[l].n
+        nbr = lambda src, w: Seg(src, w, g.nbr, g.nbr_mask)   # noqa: E731
+        conv = functools.partial(sparse.conv, n_out=n, c_out=c, mode=mode)
+        b0, b1 = p + '.blocks.block0.conv_branch', p + '.blocks.block1.conv_branch'
+        ha = conv([nbr(xa, pk[b0 + '.2'][0])], act1=pk[b0 + '.3'])
+        y, ya = conv([nbr(ha, pk[b0 + '.5'][0])], residual=x, raw=True, act1=pk[b1 + '.0'])
+        ha = conv([nbr(ya, pk[b1 + '.2'][0])], act1=pk[b1 + '.3'])
+        if l + 1 == self.num_blocks:
+            return conv([nbr(ha, pk[b1 + '.5'][0])], residual=y, act1=ret_act)
+        t0, t1 = p + '.blocks_tail.block0', p + '.blocks_tail.block1.conv_branch'
+        s_cat, t_cat = pk[t0 + '.conv_branch.0']              # BN over the 2C concat: halves go to their producers
+        z, za_down, za_tail = conv([nbr(ha, pk[b1 + '.5'][0])], residual=y, raw=True, act1=pk[p + '.conv.0'],
+                                   act2=(s_cat[:c], t_cat[:c]))
+        gn, cn = levels[l + 1], self.planes[l + 1]
+        d, da = sparse.conv([Seg(za_down, pk[p + '.conv.2'][0], g.down_index, g.down_mask)], gn.n, cn, mode,
+                            raw=True, act1=pk[p + '.u.blocks.block0.conv_branch.0'])
+        ua = self._run_ublock(p + '.u', l + 1, d, da, levels, pk, mode, pk[p + '.deconv.0'])
+        e, ea = conv([Seg(ua, pk[p + '.deconv.2'][0], g.up_index, g.up_mask)], raw=True, act1=(s_cat[c:], t_cat[c:]))
+        wa, wi = pk[t0 + '.conv_branch.2'], pk[t0 + '.i_branch.0']
+        ha = conv([nbr(za_tail, wa[0]), nbr(ea, wa[1])], act1=pk[t0 + '.conv_branch.3'])
+        t, ta = conv([nbr(ha, pk[t0 + '.conv_branch.5'][0]), Seg(z, wi[0]), Seg(e, wi[1])], raw=True,
+                     act1=pk[t1 + '.0'])
+        ha = conv([nbr(ta, pk[t1 + '.2'][0])], act1=pk[t1 + '.3'])
+        return conv([nbr(ha, pk[t1 + '.5'][0])], residual=t, act1=ret_act)
+
+    def forward_head(self, voxel_out, v2p):
+        feats, logits, offs = sparse.heads(voxel_out, v2p, self._pack())
+        return {'backbone_feats': feats, 'semantic_prediction_logits': logits, 'offset_predictions': offs}
+
+    def get_loss(self, model_output, semantic_labels, offset_labels, masks_off, masks_sem, **kwargs):
+        dev = model_output['offset_predictions'].device
+        logits = model_output['semantic_prediction_logits'].float()
+        offs = model_output['offset_predictions'].float()
+        sem, off = point_wise_loss(logits, offs, masks_sem.to(dev), masks_off.to(dev), semantic_labels.to(dev),
+                                   offset_labels.to(dev))
+        loss_dict = {'semantic_loss': sem * LOSS_MULTIPLIER_SEMANTIC, 'offset_loss': off}
+        return sum(loss_dict.values()), loss_dict
+
+
+def point_wise_loss(semantic_prediction_logits, offset_predictions, masks_sem, masks_off, semantic_labels,
+                    offset_labels, weights=None):
+    """Masked CE (sum / count) and mean L2 offset error -- reference tree_learn/util/train.py:145-166 (stays torch)."""
+    dev = semantic_prediction_logits.device
+    masks_sem, masks_off = masks_sem.to(dev), masks_off.to(dev)
+    semantic_labels, offset_labels = semantic_labels.to(dev), offset_labels.to(dev)
+    n_sem = int(masks_sem.sum())
+    if n_sem == 0:
+        semantic_loss = 0 * semantic_prediction_logits.sum()
+    else:
+        ce = F.cross_entropy(semantic_prediction_logits[masks_sem], semantic_labels[masks_sem],
+                             reduction='sum' if weights is None else 'none')
+        semantic_loss = (ce if weights is None else (ce * weights).sum()) / n_sem
+    if int(masks_off.sum()) == 0:
+        offset_loss = 0 * offset_predictions.sum()
+    else:
+        diff = offset_predictions[masks_off] - offset_labels[masks_off]
+        offset_loss = diff.pow(2).sum(1).sqrt().mean()
+    return semantic_loss, offset_loss
+
+
+def _round_tf32(w):
+    """Round-to-nearest-even to TF32 (10 explicit mantissa bits) so the tensor core's operand truncation is exact."""
+    i = w.contiguous().view(torch.int32)
+    r = ((i + 0x0FFF + ((i >> 13) & 1)) & ~0x1FFF)
+    return r.view(torch.float32)

@@ -1,0 +1,220 @@
+"""Drop-in for the hot functions of the reference's tree_learn/util/pipeline.py: same names, argument
+meaning, dtypes, label conventions and error behaviour (numpy in / numpy out), computed by the CUDA
+library instead of pandas / scikit-learn.
+
+  get_pointwise_preds                         <- util/pipeline.py:79-109
+  ensemble                                    <- util/pipeline.py:113-141
+  get_instances / group_dbscan / group_hdbscan<- util/pipeline.py:145-191
+  make_labels_consecutive                     <- util/pipeline.py:195-206
+  assign_remaining_points_nearest_neighbor    <- util/pipeline.py:287-296
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+import tqdm
+
+from . import _lib
+from ._lib import check, ptr, stream_ptr
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        raise _lib.TreeLearnCudaError('treelearn_b200.pipeline needs a CUDA device (no CPU fallback)')
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+def _ws(nbytes, dev):
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=dev)
+
+
+def get_pointwise_preds(model, dataloader, config, logger=None):
+    """Tile loop: forward every tile, keep the inner-square rows, concatenate (util/pipeline.py:79-109)."""
+    keep = {k: [] for k in ('logits', 'sem', 'off', 'off_lab', 'coords', 'inst', 'feats', 'in_feats')}
+    with torch.no_grad():
+        model.eval()
+        for batch in tqdm.tqdm(dataloader):
+            batch['voxel_size'] = config.voxel_size
+            try:
+                out = model(batch, return_loss=False)
+            except Exception as e:
+                if 'reach zero!!!' in str(e):
+                    if logger:
+                        logger.info('Error in forward pass due to axis size collapse to zero during contraction of '
+                                    'U-Net. If this does not happen too often, the results should not be influenced.')
+                    continue
+                raise
+            inner = batch['masks_inner']
+            dev_inner = inner.to(out['offset_predictions'].device)
+            # crop on the device, then a single D2H of the inner rows only (the reference copies whole tiles)
+            keep['off'].append(out['offset_predictions'][dev_inner].cpu())
+            keep['logits'].append(out['semantic_prediction_logits'][dev_inner].cpu())
+            keep['feats'].append(out['backbone_feats'][dev_inner].cpu())
+            keep['coords'].append((batch['coords'] + batch['centers'])[inner])
+            keep['in_feats'].append(batch['input_feats'][inner])
+            keep['sem'].append(batch['semantic_labels'][inner])
+            keep['off_lab'].append(batch['offset_labels'][inner])
+            keep['inst'].append(batch['instance_labels'][inner])
+    cat = {k: torch.cat(v, 0).numpy() for k, v in keep.items()}
+    return (cat['logits'], cat['sem'], cat['off'], cat['off_lab'], cat['coords'], cat['inst'], cat['feats'],
+            cat['in_feats'])
+
+
+def ensemble(coords, semantic_scores, semantic_labels, offset_predictions, offset_labels, instance_labels, feats,
+             input_feats):
+    """Overlap merge: group rows by round(coords, 2), mean of every column, sorted by (x,y,z)."""
+    lib = _lib.load()
+    dev = _dev()
+    n = len(coords)
+    cols = [np.asarray(semantic_scores, np.float32).reshape(n, -1),
+            np.asarray(semantic_labels).reshape(n, 1).astype(np.float32),
+            np.asarray(offset_predictions, np.float32).reshape(n, -1),
+            np.asarray(offset_labels, np.float32).reshape(n, -1),
+            np.asarray(instance_labels).reshape(n, 1).astype(np.float32),
+            np.asarray(feats, np.float32).reshape(n, -1), np.asarray(input_feats, np.float32).reshape(n, -1)]
+    widths = [c.shape[1] for c in cols]
+    vals = torch.from_numpy(np.ascontiguousarray(np.concatenate(cols, axis=1))).to(dev)
+    xyz = torch.from_numpy(np.ascontiguousarray(coords, dtype=np.float32)).to(dev)
+    nv = vals.shape[1]
+    out_xyz = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    out_vals = torch.empty((n, nv), dtype=torch.float32, device=dev)
+    gid = torch.empty(n, dtype=torch.int32, device=dev)
+    ng = C.c_int64(0)
+    wsb = lib.tl_merge_workspace_bytes(n)
+    ws = _ws(wsb, dev)
+    check(lib.tl_merge_groupby_mean(ptr(xyz), ptr(vals), n, nv, ptr(out_xyz), ptr(out_vals), ptr(gid), C.byref(ng),
+                                    ptr(ws), wsb, stream_ptr()))
+    ng = ng.value
+    out = out_vals[:ng].cpu().numpy()
+    parts = np.split(out, np.cumsum(widths)[:-1], axis=1)
+    return (out_xyz[:ng].cpu().numpy(), parts[0], parts[1].astype(np.int64).flatten(), parts[2], parts[3],
+            parts[4].astype(np.int64).flatten(), parts[5], parts[6])
+
+
+def make_labels_consecutive(labels, start_num):
+    palette = np.unique(labels)
+    new = np.searchsorted(palette, labels) + start_num
+    return new, {i + start_num: orig for i, orig in enumerate(palette)}
+
+
+def group_dbscan_cuda(points_xy, radius, npoint_thr, not_assigned_label, start_num_preds):
+    """Device-resident form: points_xy [n,2] f32 CUDA tensor -> (labels [n] i64 CUDA tensor, n_clusters)."""
+    lib = _lib.load()
+    n = int(points_xy.shape[0])
+    dev = points_xy.device
+    labels = torch.empty(n, dtype=torch.int64, device=dev)
+    if n == 0:
+        return labels, 0
+    pts = points_xy.contiguous().float()
+    nc = C.c_int64(0)
+    wsb = lib.tl_cluster_workspace_bytes(n)
+    ws = _ws(wsb, dev)
+    check(lib.tl_cluster_radius_cc(ptr(pts), n, float(radius), int(npoint_thr), int(not_assigned_label),
+                                   int(start_num_preds), ptr(labels), C.byref(nc), ptr(ws), wsb, stream_ptr()))
+    return labels, nc.value
+
+
+def group_dbscan(cluster_coords, radius, npoint_thr, not_assigned_label_in_grouping, start_num_preds):
+    """DBSCAN(eps=radius, min_samples=2) + size filter + consecutive relabel, as one GPU op."""
+    dev = _dev()
+    if len(cluster_coords) == 0:
+        return np.zeros(0, dtype=np.int64)
+    pts = torch.from_numpy(np.ascontiguousarray(cluster_coords[:, :2], dtype=np.float32)).to(dev)
+    labels, _ = group_dbscan_cuda(pts, radius, npoint_thr, not_assigned_label_in_grouping, start_num_preds)
+    return labels.cpu().numpy()
+
+
+def group_hdbscan(cluster_coords, npoint_thr, not_assigned_label_in_grouping, start_num_preds):
+    raise NotImplementedError(
+        'treelearn_b200: GPU HDBSCAN (SURVEY.md §8 f1) is not built yet and there is no CPU fallback; '
+        'set grouping.use_hdbscan: False to use the DBSCAN-equivalent GPU clustering')
+
+
+def get_instances(coords, offset, semantic_prediction_logits, grouping_cfg, verticality_feat, tree_class_in_dataset,
+                  non_trees_label_in_grouping, not_assigned_label_in_grouping, start_num_preds):
+    cluster_coords = (coords + offset)[:, :3]
+    probs = torch.from_numpy(semantic_prediction_logits).float().softmax(dim=-1)
+    tree_mask = (probs[:, tree_class_in_dataset] >= grouping_cfg.tree_conf_thresh).numpy()
+    vertical_mask = verticality_feat > grouping_cfg.tau_vert
+    offset_mask = np.abs(offset[:, 2]) < grouping_cfg.tau_off
+    ind_cluster = np.where(tree_mask & vertical_mask & offset_mask)[0]
+    filtered = cluster_coords[ind_cluster][:, :2]
+    predictions = non_trees_label_in_grouping * np.ones(len(cluster_coords))
+    predictions[tree_mask] = not_assigned_label_in_grouping
+    if grouping_cfg.use_hdbscan:
+        pred = group_hdbscan(filtered, grouping_cfg.tau_min, not_assigned_label_in_grouping, start_num_preds)
+    else:
+        pred = group_dbscan(filtered, grouping_cfg.tau_group, grouping_cfg.tau_min, not_assigned_label_in_grouping,
+                            start_num_preds)
+    predictions[ind_cluster] = pred
+    return predictions.astype(np.int64)
+
+
+def assign_remaining_points_nearest_neighbor(coords, predictions, remaining_points_idx, n_neighbors=5):
+    lib = _lib.load()
+    dev = _dev()
+    predictions = np.copy(predictions)
+    assert len(coords) == len(predictions)
+    query_idx = np.argwhere(predictions == remaining_points_idx).reshape(-1)
+    reference_idx = np.argwhere(predictions != remaining_points_idx).reshape(-1)
+    if len(query_idx) == 0:
+        return predictions.astype(np.int64)
+    ref = torch.from_numpy(np.ascontiguousarray(coords[reference_idx], dtype=np.float32)).to(dev)
+    lab = torch.from_numpy(np.ascontiguousarray(predictions[reference_idx]).astype(np.int64)).to(dev)
+    qry = torch.from_numpy(np.ascontiguousarray(coords[query_idx], dtype=np.float32)).to(dev)
+    predictions[query_idx] = knn_vote_cuda(ref, lab, qry, n_neighbors).cpu().numpy()
+    return predictions.astype(np.int64)
+
+
+def knn_vote_cuda(ref_xyz, ref_labels, query_xyz, n_neighbors=5):
+    """Device-resident kNN majority vote: ref [R,3] f32, labels [R] i64, query [Q,3] f32 -> [Q] i64."""
+    lib = _lib.load()
+    nr, nq = int(ref_xyz.shape[0]), int(query_xyz.shape[0])
+    out = torch.empty(nq, dtype=torch.int64, device=query_xyz.device)
+    if nq == 0:
+        return out
+    ref_xyz, ref_labels, query_xyz = ref_xyz.contiguous().float(), ref_labels.contiguous().long(), query_xyz.contiguous().float()
+    wsb = lib.tl_knn_workspace_bytes(nr, nq)
+    ws = _ws(wsb, query_xyz.device)
+    check(lib.tl_knn_vote(ptr(ref_xyz), ptr(ref_labels), nr, ptr(query_xyz), nq, int(n_neighbors), ptr(out), ptr(ws),
+                          wsb, stream_ptr()))
+    return out
+
+
+def instances_cuda(coords, offsets, logits, verticality, grouping_cfg, tree_class=0, non_trees_label=0,
+                   not_assigned_label=-1, start_num_preds=1, n_neighbors=5):
+    """Device-resident `get_instances` (DBSCAN branch) + `assign_remaining_points_nearest_neighbor` exactly as
+    tools/pipeline/pipeline.py:89-94 chains them; all inputs CUDA tensors, returns (labels [P] i64 CUDA, n_clusters)."""
+    if grouping_cfg.use_hdbscan:
+        group_hdbscan(None, None, None, None)
+    shifted = coords + offsets
+    tree_mask = logits.float().softmax(dim=-1)[:, tree_class] >= grouping_cfg.tree_conf_thresh
+    mask = tree_mask & (verticality > grouping_cfg.tau_vert) & (offsets[:, 2].abs() < grouping_cfg.tau_off)
+    ind = mask.nonzero().squeeze(1)
+    pred = torch.full((coords.shape[0],), non_trees_label, dtype=torch.int64, device=coords.device)
+    pred[tree_mask] = not_assigned_label
+    lab, n_clusters = group_dbscan_cuda(shifted[ind][:, :2], grouping_cfg.tau_group, grouping_cfg.tau_min,
+                                        not_assigned_label, start_num_preds)
+    pred[ind] = lab
+    tree_idx = (pred != non_trees_label).nonzero().squeeze(1)
+    tp = pred[tree_idx]
+    q = (tp == not_assigned_label).nonzero().squeeze(1)
+    r = (tp != not_assigned_label).nonzero().squeeze(1)
+    if q.numel() and r.numel() >= n_neighbors:
+        sh = shifted[tree_idx]
+        tp[q] = knn_vote_cuda(sh[r], tp[r], sh[q], n_neighbors)
+        pred[tree_idx] = tp
+    return pred, n_clusters
+
+
+def segment_tile(model, batch, grouping_cfg):
+    """Public per-tile call used by bench.py's e2e leg: host batch dict in (pinned or pageable), network forward,
+    offset-shifted clustering and remaining-point assignment on the device, instance labels out on the host."""
+    with torch.no_grad():
+        out = model(batch, return_loss=False)
+        dev = out['offset_predictions'].device
+        coords = batch['coords'].to(dev, non_blocking=True)
+        vert = batch['input_feats'].to(dev, non_blocking=True)[:, -1]
+        labels, n_clusters = instances_cuda(coords, out['offset_predictions'], out['semantic_prediction_logits'], vert,
+                                            grouping_cfg)
+        return labels.to(torch.int32).cpu().numpy(), n_clusters

@@ -1,0 +1,196 @@
+"""Host side of the hash-indexed sparse voxel tensor: point->voxel, level pyramid, rulebooks.
+
+Replaces what `spconv.SparseConvTensor` + `indice_dict` carry in the reference
+(tree_learn/model/tree_learn.py:88).  Rows of every level are kept
+in Morton order (batch-major), so the 2^3 children of a coarse voxel are adjacent rows and
+3^3 neighbours are close in memory; the reference leaves the row order implementation-defined.
+torch only provides device memory and the stream.
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import torch
+
+from . import _lib
+from ._lib import check, ptr, stream_ptr, TILE_ROWS
+
+
+def pad_rows(n):
+    return (n + TILE_ROWS - 1) // TILE_ROWS * TILE_ROWS
+
+
+def _workspace(nbytes, device):
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+@dataclass
+class Level:
+    n: int                       # active voxels
+    shape: List[int]             # spatial shape (x,y,z) at this level
+    keys: torch.Tensor           # [n] int64 view of the u64 Morton keys, ascending
+    coords: torch.Tensor         # [n,4] int32 (b,x,y,z)
+    nbr: Optional[torch.Tensor] = None        # [27, pad(n)] int32
+    nbr_mask: Optional[torch.Tensor] = None   # [pad(n)/128] int32 bitmask
+    down_index: Optional[torch.Tensor] = None  # [8, stride] rows of THIS level feeding the next (coarser) level
+    down_mask: Optional[torch.Tensor] = None
+    up_index: Optional[torch.Tensor] = None    # [8, stride] rows of the next level feeding THIS level
+    up_mask: Optional[torch.Tensor] = None
+    pair_stride: int = 0
+
+    @property
+    def nbr_stride(self):
+        return pad_rows(self.n)
+
+
+def voxelize(coords, input_feats, batch_ids, batch_size, voxel_size=0.1, use_coords=False, use_feats=True,
+             max_num_points_per_voxel=3):
+    """coords [N,3] f32, input_feats [N,F] f32, batch_ids [N] i64 ascending (all CUDA).
+    Returns (voxel_feats [M,F+3] as [feat...,x,y,z], voxel_coords [M,4] i32, keys [M] i64, v2p [N] i64)."""
+    lib = _lib.load()
+    _lib.require_cuda(coords, input_feats, batch_ids)
+    coords = coords.contiguous().float()
+    n = coords.shape[0]
+    f = 0 if input_feats is None else input_feats.shape[1]
+    feats = None if f == 0 else input_feats.contiguous().float()
+    bids = batch_ids.contiguous().long()
+    dev = coords.device
+    keys = torch.empty(n, dtype=torch.int64, device=dev)
+    vcoords = torch.empty((n, 4), dtype=torch.int32, device=dev)
+    vfeats = torch.empty((n, f + 3), dtype=torch.float32, device=dev)
+    v2p = torch.empty(n, dtype=torch.int64, device=dev)
+    m = C.c_int64(0)
+    wsb = lib.tl_voxelize_workspace_bytes(n)
+    ws = _workspace(wsb, dev)
+    check(lib.tl_voxelize(ptr(coords), ptr(feats), f, ptr(bids), n, int(batch_size), float(voxel_size),
+                          int(bool(use_coords)), int(bool(use_feats)), int(max_num_points_per_voxel),
+                          ptr(keys), ptr(vcoords), ptr(vfeats), ptr(v2p), C.byref(m), ptr(ws), wsb, stream_ptr()))
+    m = m.value
+    return vfeats[:m], vcoords[:m], keys[:m], v2p
+
+
+def build_levels(keys, coords, spatial_shape, num_levels, subm=True):
+    """Level pyramid (strided k2/s2 maps) + 3^3 rulebook per level.  Raises ValueError('... reach zero!!! ...')
+    like spconv when an axis of the U-Net collapses (tree_learn/util/pipeline.py:91-97)."""
+    lib = _lib.load()
+    dev = keys.device
+    levels = [Level(n=int(keys.shape[0]), shape=[int(s) for s in spatial_shape], keys=keys, coords=coords)]
+    for l in range(num_levels - 1):
+        fine = levels[-1]
+        n = fine.n
+        stride = pad_rows(n)
+        ckeys = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+        ccoords = torch.empty((max(n, 1), 4), dtype=torch.int32, device=dev)
+        fine.down_index = torch.empty((8, stride), dtype=torch.int32, device=dev)
+        fine.up_index = torch.empty((8, stride), dtype=torch.int32, device=dev)
+        fine.down_mask = torch.empty(stride // TILE_ROWS, dtype=torch.int32, device=dev)
+        fine.up_mask = torch.empty(stride // TILE_ROWS, dtype=torch.int32, device=dev)
+        fine.pair_stride = stride
+        fshape = (C.c_int32 * 3)(*fine.shape)
+        cshape = (C.c_int32 * 3)()
+        nc = C.c_int64(0)
+        if n == 0:
+            cs = [(s - 2) // 2 + 1 for s in fine.shape]
+            if min(cs) <= 0:
+                raise ValueError(f'your out spatial shape {cs} reach zero!!! input shape: {fine.shape}')
+            levels.append(Level(n=0, shape=cs, keys=ckeys[:0], coords=ccoords[:0]))
+            continue
+        wsb = lib.tl_level_workspace_bytes(n)
+        ws = _workspace(wsb, dev)
+        check(lib.tl_build_level(ptr(fine.keys), n, fshape, ptr(ckeys), ptr(ccoords), ptr(fine.down_index),
+                                 ptr(fine.down_mask), ptr(fine.up_index), ptr(fine.up_mask), cshape, C.byref(nc),
+                                 ptr(ws), wsb, stream_ptr()))
+        levels.append(Level(n=nc.value, shape=list(cshape), keys=ckeys[:nc.value], coords=ccoords[:nc.value]))
+    if subm:
+        for lv in levels:
+            build_subm_rulebook(lv)
+    return levels
+
+
+def build_subm_rulebook(lv):
+    lib = _lib.load()
+    dev = lv.keys.device
+    stride = pad_rows(lv.n)
+    lv.nbr = torch.empty((27, max(stride, TILE_ROWS)), dtype=torch.int32, device=dev)
+    lv.nbr_mask = torch.empty(max(stride // TILE_ROWS, 1), dtype=torch.int32, device=dev)
+    if lv.n == 0:
+        return lv
+    wsb = lib.tl_rulebook_workspace_bytes(lv.n)
+    ws = _workspace(wsb, dev)
+    shape = (C.c_int32 * 3)(*lv.shape)
+    check(lib.tl_subm_rulebook(ptr(lv.keys), lv.n, shape, ptr(lv.nbr), ptr(lv.nbr_mask), ptr(ws), wsb, stream_ptr()))
+    return lv
+
+
+# ---- segmented gather-GEMM convolution -----------------------------------------------------------
+@dataclass
+class Seg:
+    src: torch.Tensor                      # [rows, c_in] f32 contiguous
+    weight: torch.Tensor                   # packed for the active mode, [n_off, ...]
+    index: Optional[torch.Tensor] = None   # [n_off, stride] i32 or None (identity)
+    mask: Optional[torch.Tensor] = None
+
+
+PROFILE = None   # bench.py sets this to a list: every conv launch appends (start_evt, end_evt, alg_bytes, flops)
+
+
+def conv(segs, n_out, c_out, mode, residual=None, raw=False, act1=None, act2=None):
+    """acc = sum_seg sum_k W[k] . src[index[k]] (+ residual); returns (raw?, act1?, act2?) tensors that were
+    asked for, in that order.  act = (scale, shift) per channel => relu(scale*v+shift)  (BN eval + ReLU)."""
+    lib = _lib.load()
+    dev = segs[0].src.device
+    d = _lib.ConvDesc()
+    d.n_out, d.c_out, d.n_seg = int(n_out), int(c_out), len(segs)
+    for i, s in enumerate(segs):
+        g = d.seg[i]
+        g.src, g.src_stride, g.c_in = ptr(s.src), s.src.stride(0), s.src.shape[1]
+        g.weight, g.n_off = ptr(s.weight), s.weight.shape[0]
+        if s.index is not None:
+            g.index, g.index_stride, g.tile_mask = ptr(s.index), s.index.stride(0), ptr(s.mask)
+    outs = []
+    d.residual = ptr(residual)
+    if raw:
+        o = torch.empty((n_out, c_out), dtype=torch.float32, device=dev)
+        d.out_raw = ptr(o)
+        outs.append(o)
+    if act1 is not None:
+        o = torch.empty((n_out, c_out), dtype=torch.float32, device=dev)
+        d.out_act1, d.scale1, d.shift1 = ptr(o), ptr(act1[0]), ptr(act1[1])
+        outs.append(o)
+    if act2 is not None:
+        o = torch.empty((n_out, c_out), dtype=torch.float32, device=dev)
+        d.out_act2, d.scale2, d.shift2 = ptr(o), ptr(act2[0]), ptr(act2[1])
+        outs.append(o)
+    if PROFILE is not None and n_out > 0:
+        # algorithmic traffic: every input row once + one output + index tables + weights
+        byts = n_out * c_out * 4
+        flops = 0
+        for s in segs:
+            byts += s.src.shape[0] * s.src.shape[1] * 4 + s.weight.numel() * 4
+            if s.index is not None:
+                byts += s.weight.shape[0] * n_out * 4
+            flops += 2 * s.weight.shape[0] * n_out * s.src.shape[1] * c_out    # dense upper bound (all offsets present)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(lib.tl_conv_fwd(C.byref(d), int(mode), stream_ptr()))
+        e1.record()
+        PROFILE.append((e0, e1, byts, flops, c_out))
+    else:
+        check(lib.tl_conv_fwd(C.byref(d), int(mode), stream_ptr()))
+    return outs[0] if len(outs) == 1 else tuple(outs)
+
+
+def heads(voxel_feats, v2p, packed):
+    """voxel->point gather + both 2-layer heads (tree_learn.py:97-103).  packed: dict of folded weights."""
+    lib = _lib.load()
+    n = int(v2p.shape[0])
+    c = int(voxel_feats.shape[1])
+    dev = voxel_feats.device
+    feats = torch.empty((n, c), dtype=torch.float32, device=dev)
+    logits = torch.empty((n, 2), dtype=torch.float32, device=dev)
+    offs = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    check(lib.tl_heads_fwd(ptr(voxel_feats), ptr(v2p), n, c, ptr(packed['sem_w1']), ptr(packed['sem_b1']),
+                           ptr(packed['sem_w2']), ptr(packed['sem_b2']), ptr(packed['off_w1']), ptr(packed['off_b1']),
+                           ptr(packed['off_w2']), ptr(packed['off_b2']), ptr(feats), ptr(logits), ptr(offs),
+                           stream_ptr()))
+    return feats, logits, offs

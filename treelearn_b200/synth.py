@@ -105,3 +105,17 @@ WORKLOADS = {
 
 def workload(name):
     return synth_forest(**WORKLOADS[name])
+
+
+def randomize_bn_stats(model, seed=0):
+    """Random-init weights keep BN as identity; randomise affine + running stats so BN is not a no-op."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm1d):
+                c = m.num_features
+                m.weight.copy_(0.5 + torch.rand(c, generator=g))
+                m.bias.copy_(0.2 * torch.randn(c, generator=g))
+                m.running_mean.copy_(0.1 * torch.randn(c, generator=g))
+                m.running_var.copy_(0.5 + torch.rand(c, generator=g))
+    return model
