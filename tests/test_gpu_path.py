@@ -80,7 +80,12 @@ def test_rulebooks_bit_exact():
             out_idx, out_shape, in_row, kappa, out_row = sp.strided_pairs(coords, lv.shape)
             nxt = levels[l + 1]
             assert nxt.shape == out_shape and nxt.n == len(out_idx)
-            assert np.array_equal(nxt.coords.cpu().numpy(), out_idx), 'coarse voxels: sorted unique, same order'
+            ccoords = nxt.coords.cpu().numpy()
+            where = _key_rows(ccoords)                      # coarse row order is implementation-defined (Morton here)
+            assert set(where) == set(_key_rows(out_idx)), 'coarse voxel set'
+            assert np.all(np.diff(nxt.keys.cpu().numpy()) > 0)
+            to_mine = np.array([where[tuple(r)] for r in out_idx.tolist()])
+            out_row = to_mine[out_row]
             down = lv.down_index.cpu().numpy()
             up = lv.up_index.cpu().numpy()
             exp_down = -np.ones_like(down)
@@ -245,3 +250,78 @@ def test_cluster_and_knn_vs_oracle_random(n, seed):
         pred[:5] = np.arange(5)
         assert np.array_equal(pipeline.assign_remaining_points_nearest_neighbor(xyz, pred, -1),
                               cluster_ref.assign_remaining_ref(xyz, pred, -1))
+
+
+# ---- tcgen05 / TF32 path ---------------------------------------------------------------------------
+from treelearn_b200.model import _round_tf32  # noqa: E402
+
+TF32_EXACT_TOL = dict(atol=3e-4, rtol=2e-4)    # operands pre-rounded to TF32: only the accumulation order differs
+
+
+def _tc_weight(w, co, k, ci):
+    return _round_tf32(w.reshape(co, k, ci).permute(1, 0, 2).contiguous()).cuda()
+
+
+@pytest.mark.parametrize('ci,co', [(32, 32), (64, 32), (32, 64), (96, 96), (128, 160), (224, 224)])
+def test_tc_subm_conv_parity(ci, co):
+    batch = synth.make_batch([synth.synth_forest(edge=5.0, n_trees=2, seed=9, ground_density=200.0)])
+    (vf, vc, keys, v2p), _ = _voxelize_both(batch)
+    lv = sparse.build_levels(keys, vc, [500, 500, 1000], 1)[0]
+    g = torch.Generator().manual_seed(ci * 1000 + co)
+    x = _round_tf32(torch.randn((lv.n, ci), generator=g))
+    w = _round_tf32(torch.randn((co, 3, 3, 3, ci), generator=g) / (27 * ci) ** 0.5)
+    res = torch.randn((lv.n, co), generator=g)
+    s, t = torch.rand(co, generator=g) + 0.5, torch.randn(co, generator=g)
+    ref = model_ref._subm(x, sp.subm_neighbour_table(vc.cpu().numpy(), [500, 500, 1000]), w) + res
+    raw, act, act2 = sparse.conv([sparse.Seg(x.cuda(), _tc_weight(w, co, 27, ci), lv.nbr, lv.nbr_mask)], lv.n, co,
+                                 _lib.MODE_TF32, residual=res.cuda(), raw=True, act1=(s.cuda(), t.cuda()),
+                                 act2=(t.cuda().abs() + 0.1, s.cuda()))
+    assert torch.allclose(raw.cpu(), ref, **TF32_EXACT_TOL)
+    assert torch.allclose(act.cpu(), torch.relu(ref * s + t), atol=2e-3, rtol=1e-3)      # + TF32 rounding of the store
+    assert torch.allclose(act2.cpu(), torch.relu(ref * (t.abs() + 0.1) + s), atol=2e-3, rtol=1e-3)
+
+
+def test_tc_multi_segment_strided_inverse_parity():
+    batch = synth.make_batch([synth.synth_forest(edge=5.0, n_trees=2, seed=10, ground_density=200.0)])
+    (vf, vc, keys, v2p), _ = _voxelize_both(batch)
+    lv, nx = sparse.build_levels(keys, vc, [500, 500, 1000], 2)
+    g = torch.Generator().manual_seed(3)
+    rt = lambda *shape: _round_tf32(torch.randn(shape, generator=g))   # noqa: E731
+    x, wd, wu = rt(lv.n, 32), rt(64, 2, 2, 2, 32) / 16, rt(32, 2, 2, 2, 64) / 16
+    out_idx, out_shape, in_row, kappa, out_row = sp.strided_pairs(vc.cpu().numpy(), [500, 500, 1000])
+    where = _key_rows(nx.coords.cpu().numpy())
+    out_row = np.array([where[tuple(r)] for r in out_idx.tolist()])[out_row]
+    ref_d = model_ref._pairs_conv(x, wd, in_row, kappa, out_row, nx.n)
+    d = sparse.conv([sparse.Seg(x.cuda(), _tc_weight(wd, 64, 8, 32), lv.down_index, lv.down_mask)], nx.n, 64,
+                    _lib.MODE_TF32, raw=True)
+    assert torch.allclose(d.cpu(), ref_d, **TF32_EXACT_TOL)
+    d_r = _round_tf32(ref_d)
+    ref_u = model_ref._pairs_conv(d_r, wu, out_row, kappa, in_row, lv.n)
+    u = sparse.conv([sparse.Seg(d_r.cuda(), _tc_weight(wu, 32, 8, 64), lv.up_index, lv.up_mask)], lv.n, 32,
+                    _lib.MODE_TF32, raw=True)
+    assert torch.allclose(u.cpu(), ref_u, **TF32_EXACT_TOL)
+    # three segments: 3^3 conv + two identity (1x1) segments == blocks_tail.block0 second conv
+    h, z, e = rt(lv.n, 32), rt(lv.n, 32), rt(lv.n, 32)
+    w3, wz, we = rt(32, 3, 3, 3, 32) / 30, rt(32, 1, 1, 1, 32) / 6, rt(32, 1, 1, 1, 32) / 6
+    nbr = sp.subm_neighbour_table(vc.cpu().numpy(), [500, 500, 1000])
+    ref = model_ref._subm(h, nbr, w3) + z @ wz.reshape(32, 32).T + e @ we.reshape(32, 32).T
+    out = sparse.conv([sparse.Seg(h.cuda(), _tc_weight(w3, 32, 27, 32), lv.nbr, lv.nbr_mask),
+                       sparse.Seg(z.cuda(), _tc_weight(wz, 32, 1, 32)), sparse.Seg(e.cuda(), _tc_weight(we, 32, 1, 32))],
+                      lv.n, 32, _lib.MODE_TF32, raw=True)
+    assert torch.allclose(out.cpu(), ref, **TF32_EXACT_TOL)
+
+
+def test_tc_default_model_offsets_within_1e3_of_fp32_oracle():
+    """north_star tolerance: per-point offsets within 1e-3 of the (fp32) reference restatement, TF32 tensor cores."""
+    batch = _tile('tiny')
+    sd = model_ref.make_state_dict(channels=32, num_blocks=7, seed=0)
+    net = TreeLearn(use_feats=False, use_coords=False, spatial_shape=[500, 500, 1000], mode='tf32')
+    net.load_state_dict(sd)
+    net = net.cuda().eval()
+    with torch.no_grad():
+        mine = net(batch, return_loss=False)
+        ref = model_ref.forward_ref(sd, batch, spatial_shape=[500, 500, 1000])
+    err = (mine['offset_predictions'].cpu() - ref['offset_predictions']).abs().max().item()
+    print('tf32 offset max err', err)
+    assert err < 1e-3
+    assert (mine['semantic_prediction_logits'].cpu() - ref['semantic_prediction_logits']).abs().max() < 2e-3

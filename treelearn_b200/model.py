@@ -165,10 +165,10 @@ class TreeLearn(nn.Module):
                         pieces = [w]
                     out = []
                     for piece in pieces:
-                        if tf32:
-                            out.append(_round_tf32(piece.permute(1, 0, 2).contiguous()))   # [K, Co, Ci]
+                        if tf32 and tc_eligible(piece.shape[2], co):
+                            out.append(_round_tf32(piece.permute(1, 0, 2).contiguous()))   # [K, Co, Ci] K-major B operand
                         else:
-                            out.append(piece.permute(1, 2, 0).contiguous())               # [K, Ci, Co]
+                            out.append(piece.permute(1, 2, 0).contiguous())               # [K, Ci, Co] SIMT layout
                     pk[name] = out
                 elif isinstance(m, nn.BatchNorm1d) and not name.startswith(('semantic_linear', 'offset_linear')):
                     s = (m.weight / torch.sqrt(m.running_var + m.eps)).float()
@@ -277,6 +277,11 @@ def point_wise_loss(semantic_prediction_logits, offset_predictions, masks_sem, m
         diff = offset_predictions[masks_off] - offset_labels[masks_off]
         offset_loss = diff.pow(2).sum(1).sqrt().mean()
     return semantic_loss, offset_loss
+
+
+def tc_eligible(c_in, c_out):
+    """Same rule as csrc/tl_conv_tc.cu: the tcgen05 path takes 32-channel K blocks and N = C_out <= 256."""
+    return c_in % 32 == 0 and c_out % 32 == 0 and c_out <= 256
 
 
 def _round_tf32(w):
