@@ -97,6 +97,7 @@ typedef struct {
     float* out_act2;
     const float* scale2;
     const float* shift2;
+    float* splitk_ws; /* optional [n_out, c_out] fp32 scratch: lets layers with few row tiles run split-K */
 } tl_conv_desc;
 
 #define TL_MODE_FP32 0

@@ -327,3 +327,20 @@ def test_tc_default_model_offsets_within_1e3_of_fp32_oracle():
     print('tf32 offset max err', err)
     assert err < 1e-3
     assert (mine['semantic_prediction_logits'].cpu() - ref['semantic_prediction_logits']).abs().max() < 2e-3
+
+
+def test_tc_matches_fp32_path_on_larger_tile():
+    """No split-K at level 0 here (> 2 waves of tiles): the fused-epilogue tcgen05 path vs the fp32 SIMT path."""
+    batch = _tile('small')
+    sd = model_ref.make_state_dict(channels=32, num_blocks=7, seed=1)
+    outs = {}
+    for mode in ('fp32', 'tf32'):
+        net = TreeLearn(use_feats=False, use_coords=False, spatial_shape=[500, 500, 1000], mode=mode)
+        net.load_state_dict(sd)
+        net = net.cuda().eval()
+        with torch.no_grad():
+            outs[mode] = net(batch, return_loss=False)
+    err = (outs['tf32']['offset_predictions'] - outs['fp32']['offset_predictions']).abs().max().item()
+    print('tf32 vs fp32 offsets', err)
+    assert err < 1e-3
+    assert (outs['tf32']['semantic_prediction_logits'] - outs['fp32']['semantic_prediction_logits']).abs().max() < 2e-3

@@ -28,7 +28,7 @@ class ConvDesc(C.Structure):
     _fields_ = [('n_out', C.c_int32), ('c_out', C.c_int32), ('n_seg', C.c_int32), ('reserved', C.c_int32),
                 ('seg', ConvSeg * TL_MAX_SEG), ('residual', C.c_void_p), ('out_raw', C.c_void_p),
                 ('out_act1', C.c_void_p), ('scale1', C.c_void_p), ('shift1', C.c_void_p),
-                ('out_act2', C.c_void_p), ('scale2', C.c_void_p), ('shift2', C.c_void_p)]
+                ('out_act2', C.c_void_p), ('scale2', C.c_void_p), ('shift2', C.c_void_p), ('splitk_ws', C.c_void_p)]
 
 
 _P, _I32, _I64, _F, _D, _SZ = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double, C.c_size_t

@@ -131,6 +131,7 @@ class Seg:
     mask: Optional[torch.Tensor] = None
 
 
+SPLITK_MAX_ROWS = 2 * 148 * TILE_ROWS   # below two waves of 128-row tiles the library may split K over CTAs
 PROFILE = None   # bench.py sets this to a list: every conv launch appends (start_evt, end_evt, alg_bytes, flops)
 
 
@@ -161,6 +162,9 @@ def conv(segs, n_out, c_out, mode, residual=None, raw=False, act1=None, act2=Non
         o = torch.empty((n_out, c_out), dtype=torch.float32, device=dev)
         d.out_act2, d.scale2, d.shift2 = ptr(o), ptr(act2[0]), ptr(act2[1])
         outs.append(o)
+    if mode == _lib.MODE_TF32 and 0 < n_out < SPLITK_MAX_ROWS:
+        ws = torch.empty((n_out, c_out), dtype=torch.float32, device=dev)   # deep levels: few tiles -> split-K scratch
+        d.splitk_ws = ptr(ws)
     if PROFILE is not None and n_out > 0:
         # algorithmic traffic: every input row once + one output + index tables + weights
         byts = n_out * c_out * 4
