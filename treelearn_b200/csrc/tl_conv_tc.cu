@@ -29,13 +29,17 @@ constexpr int BM = 128;          // rows per tile == TMEM lanes
 constexpr int BK = 32;           // fp32 elements per K block == one 128 B swizzle row
 constexpr int MAX_STAGES = 12;
 constexpr int A_STAGE_BYTES = BM * 128;
-constexpr int kProducerWarps = 8;        // two groups of four; a group fills one whole stage
+constexpr int kMaxGroups = 4;            // producer groups of four warps; group g fills the chunks with ordinal % G == g
+constexpr int kProducerWarps = 4 * kMaxGroups;
 constexpr int kProducerThreads = 128;    // arrivals per stage (one group)
 constexpr int kEpilogueThreads = 128;
-constexpr int kMmaWarp = kProducerWarps + 4;
-constexpr int kThreads = 32 * (kProducerWarps + 4 + 1);
+constexpr int kFirstEpilogueWarp = kProducerWarps;      // 16..19: warp % 4 == TMEM lane quarter
+constexpr int kMmaWarp = kProducerWarps + 4;            // 20
+constexpr int kSchedWarp = kProducerWarps + 5;          // 21: builds each work item's descriptor (rulebook rows + chunk list)
+constexpr int kThreads = 32 * (kProducerWarps + 4 + 2);
+constexpr int MAX_CHUNKS = 448;                         // live (segment, offset, k-block) entries per work item
 constexpr int IDX_ROWS = 32;                         // rulebook rows (segment, offset) staged per tile
-constexpr int IDX_BUF_BYTES = IDX_ROWS * BM * 4;     // one tile's worth; double buffered
+constexpr int IDX_BUF_BYTES = IDX_ROWS * BM * 4 + MAX_CHUNKS * 4 + 64;   // rulebook rows + chunk list + count; x2
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -61,6 +65,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
+__device__ __forceinline__ void cp_async16_cg(uint32_t dst, const void* src, uint32_t src_bytes) {   // L2 only
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
@@ -68,6 +75,10 @@ __device__ __forceinline__ int ld_shared_i32(uint32_t addr) {
     int v;
     asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
+}
+// the mbarrier is arrived on (without bumping its pending count) once all prior cp.async of this thread completed
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 // wait until at most `n` of this thread's cp.async groups are pending (n is warp-uniform)
@@ -145,8 +156,12 @@ struct Launch {   // per-launch scalars (kernel parameter)
     int splits;        // CTAs sharing one tile's K range (1 = fused epilogue)
     int chunks_total;  // (segment, offset, k-block) ordinals per tile, masked ones included
     int stages, lag;
-    int tmem_cols, buf_cols;
+    int tmem_cols, buf_cols;   // TMEM columns allocated / per accumulator buffer (two buffers)
+    int debug;                 // timing experiments only: 1 = skip MMAs, 2 = skip A gather, 4 = skip epilogue memory ops, 8 = skip B copy
+    int acc_ways, acc_cols;    // independent accumulators per buffer (K-step kk -> accumulator kk % ways) and their stride
     float* splitk_ws;  // [n_out, c_out] zeroed fp32 accumulation buffer when splits > 1
+    int groups;        // active producer groups (power of two <= kMaxGroups, < stages)
+    int use_cg;        // gather A rows with cp.async.cg (bypass L1) instead of .ca
     int idx_base[TL_MAX_SEG];   // first prefetch row of each indexed segment (segments sharing a table share rows)
     int idx_owner[TL_MAX_SEG];  // 1 = this segment's table rows are fetched (0 = alias of an earlier segment)
 };
@@ -163,6 +178,14 @@ struct Layout {  // dynamic shared memory carve-up (1024 B aligned base)
     __device__ __forceinline__ uint32_t empty(uint32_t s) const { return empty0 + 8 * s; }
     __device__ __forceinline__ uint32_t tfull(uint32_t b) const { return tfull0 + 8 * b; }
     __device__ __forceinline__ uint32_t tempty(uint32_t b) const { return tempty0 + 8 * b; }
+    __device__ __forceinline__ uint32_t wfull(uint32_t b) const { return tempty0 + 16 + 8 * b; }
+    __device__ __forceinline__ uint32_t wempty(uint32_t b) const { return tempty0 + 32 + 8 * b; }
+    __device__ __forceinline__ uint32_t list(uint32_t buf, int j) const {
+        return idx0 + buf * IDX_BUF_BYTES + IDX_ROWS * BM * 4 + (uint32_t)j * 4u;
+    }
+    __device__ __forceinline__ uint32_t count(uint32_t buf) const {
+        return idx0 + buf * IDX_BUF_BYTES + IDX_ROWS * BM * 4 + MAX_CHUNKS * 4;
+    }
 };
 
 __device__ __forceinline__ Layout carve(uint32_t base, int n, int stages) {
@@ -176,11 +199,11 @@ __device__ __forceinline__ Layout carve(uint32_t base, int n, int stages) {
     L.empty0 = off + 8 * MAX_STAGES;
     L.tfull0 = off + 16 * MAX_STAGES;
     L.tempty0 = L.tfull0 + 16;
-    L.tmem_slot = L.tfull0 + 32;
+    L.tmem_slot = L.tfull0 + 64;
     return L;
 }
 static inline size_t smem_bytes(int n, int stages) {
-    return 1024 + (size_t)stages * (A_STAGE_BYTES + (size_t)n * 128) + 2 * IDX_BUF_BYTES + 16 * MAX_STAGES + 64;
+    return 1024 + (size_t)stages * (A_STAGE_BYTES + (size_t)n * 128) + 2 * IDX_BUF_BYTES + 16 * MAX_STAGES + 128;
 }
 
 __device__ __forceinline__ uint32_t seg_mask(const tl_conv_seg& sg, int64_t tile) {
@@ -189,29 +212,21 @@ __device__ __forceinline__ uint32_t seg_mask(const tl_conv_seg& sg, int64_t tile
     return (sg.tile_mask ? sg.tile_mask[tile] : 0xffffffffu) & all;
 }
 
-// Enumerate the live chunks of (tile, split): f(seg, k, kb, new_offset) for ordinals in [lo, hi) whose offset is
-// in the tile's mask.  Producer and MMA threads run the identical enumeration.
-template <typename F>
-__device__ __forceinline__ void for_each_chunk(const tl_conv_desc& d, int tile, int lo, int hi, F&& f) {
-    int ord = 0;
-    for (int s = 0; s < d.n_seg; ++s) {
-        const tl_conv_seg& sg = d.seg[s];
-        const uint32_t mask = seg_mask(sg, tile);
-        const int kblocks = sg.c_in / BK;
-        for (int k = 0; k < sg.n_off; ++k, ord += kblocks) {
-            if (ord >= hi) return;
-            if (ord + kblocks <= lo || !((mask >> k) & 1u)) continue;
-            bool fresh = true;
-            for (int kb = 0; kb < kblocks; ++kb) {
-                const int o = ord + kb;
-                if (o < lo || o >= hi) continue;
-                f(s, k, kb, fresh);
-                fresh = false;
-            }
-        }
-    }
+__device__ __forceinline__ void st_shared_u32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
 }
 
+// Warp roles (704 threads, one CTA per SM, persistent over work items = (row tile, K split)):
+//   warps  0..15  producers: G groups of 4 warps; group g fills the chunks whose ordinal in the CTA's stream is g mod G
+//   warps 16..19  epilogue (TMEM lane quarter = warp % 4)
+//   warp  20      MMA issuer (lane 0) + TMEM alloc/dealloc
+//   warp  21      scheduler: one work item ahead it stages the item's rulebook rows (cp.async) and the list of live
+//                 (segment, offset, k-block) chunks in shared memory, so nobody else evaluates masks or split ranges
 __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const tl_conv_desc d, const Launch P) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -231,6 +246,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const tl_conv_desc d, c
         for (int b = 0; b < 2; ++b) {
             mbar_init(L.tfull(b), 1);
             mbar_init(L.tempty(b), kEpilogueThreads);
+            mbar_init(L.wfull(b), 33);                               // 32 cp.async completions + lane 0
+            mbar_init(L.wempty(b), 128 * P.groups + kEpilogueThreads + 1);   // every reader of the descriptor
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -245,15 +262,58 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const tl_conv_desc d, c
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
-    if (warp < kProducerWarps) {
+    if (warp == kSchedWarp) {
+        // ===================== scheduler: work-item descriptors ====================================
+        uint32_t witer = 0;
+        for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++witer) {
+            const uint32_t buf = witer & 1u;
+            if (witer >= 2) mbar_wait(L.wempty(buf), ((witer >> 1) - 1u) & 1u);   // readers of item witer-2 are done
+            const int tile = w / P.splits, split = w - tile * P.splits;
+            const int lo = split * per_split, hi = min(lo + per_split, P.chunks_total);
+            int ord = 0, pos = 0;
+            for (int s = 0; s < d.n_seg; ++s) {
+                const tl_conv_seg& sg = d.seg[s];
+                const int kblocks = sg.c_in / BK;
+                if (sg.index && P.idx_owner[s]) {   // rulebook rows: lane stages 4 tile rows (16 B) per offset
+                    const int32_t* ip = sg.index + (int64_t)tile * BM + 4 * lane;
+                    for (int k = 0; k < sg.n_off; ++k)
+                        cp_async16(L.idx(buf, P.idx_base[s] + k, 4 * lane), ip + (int64_t)k * sg.index_stride, 16u);
+                }
+                // lane k owns offset k: live k-blocks inside [lo, hi), exclusive prefix over lanes = list position
+                const uint32_t mask = seg_mask(sg, tile);
+                const int o = ord + lane * kblocks;
+                int kb_lo = 0, cnt = 0;
+                if (lane < sg.n_off && ((mask >> lane) & 1u)) {
+                    kb_lo = max(lo - o, 0);
+                    cnt = max(min(hi - o, kblocks) - kb_lo, 0);
+                }
+                int incl = cnt;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, incl, off);
+                    if (lane >= off) incl += v;
+                }
+                const int mypos = pos + incl - cnt;
+                for (int t = 0; t < cnt; ++t)
+                    if (mypos + t < MAX_CHUNKS)
+                        st_shared_u32(L.list(buf, mypos + t), (uint32_t)((s << 8) | (lane << 3) | (kb_lo + t)));
+                pos += __shfl_sync(0xffffffffu, incl, 31);
+                ord += sg.n_off * kblocks;
+            }
+            if (lane == 0) st_shared_u32(L.count(buf), (uint32_t)min(pos, MAX_CHUNKS));
+            __syncwarp();
+            cp_async_mbar_arrive_noinc(L.wfull(buf));
+            if (lane == 0) mbar_arrive(L.wfull(buf));
+        }
+    } else if (warp < 4 * P.groups) {
         // ===================== producers: gather A rows + copy B slab ==============================
-        // Two groups of 4 warps take alternate chunks (the loop is issue/latency bound per warp, so two warps per
-        // SM sub-partition double the rate).  Everything loop-invariant is hoisted: per-thread swizzled destination
-        // offsets, per-(segment, offset) row pointers; ring position is tracked incrementally (no div/mod).
+        // A thread never waits for its copies: `cp.async.mbarrier.arrive.noinc` makes the stage's full barrier count
+        // this thread once all its prior cp.async have landed (the CUTLASS sm100 cp.async->UMMA hand-off), so up to S
+        // chunks are in flight per CTA.
         const int group = warp >> 2, gw = warp & 3;       // producer group, warp within group
         const int ptid = threadIdx.x & 127;               // thread within group
         const int chunk = lane & 7, sub = lane >> 3;
-        const int col = gw * 32 + lane;                   // the tile row whose rulebook entry this thread stages
+        const int col = gw * 32 + lane;                   // tile row whose rulebook entry this thread reads
         uint32_t a_off[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -263,122 +323,92 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const tl_conv_desc d, c
         const int brow = ptid >> 3;                       // B rows brow + 16 j
         const uint32_t b_off0 = (uint32_t)(brow * 128 + ((chunk ^ (brow & 7)) << 4));
         const int nb = N >> 4;
-        const uint32_t lag = (uint32_t)P.lag;
-
-        auto prefetch_idx = [&](int tile, uint32_t buf) {   // group 0 only
-            for (int s = 0; s < d.n_seg; ++s) {
-                const tl_conv_seg& sg = d.seg[s];
-                if (!sg.index || !P.idx_owner[s]) continue;
-                const int32_t* ip = sg.index + (int64_t)tile * BM + col;
-                for (int k = 0; k < sg.n_off; ++k) cp_async4(L.idx(buf, P.idx_base[s] + k, col), ip + (int64_t)k * sg.index_stride);
-            }
-            cp_async_commit();
-        };
-
-        uint32_t slot = 0, phase = 0;          // ring position of the next chunk (all chunks, both groups)
-        uint32_t cidx = 0;                     // chunk ordinal in this CTA's stream: owner = cidx & 1
-        uint32_t own_issued = 0, own_pub = 0;  // this group's chunks issued / published
-        uint32_t pub_slot = (uint32_t)group % S;   // ring slot of this group's next chunk to publish
-        uint32_t witer = 0, since_prefetch = 0;
-        if (group == 0 && (int)blockIdx.x < num_work) prefetch_idx((int)blockIdx.x / P.splits, 0);
+        const uint32_t G = (uint32_t)P.groups;
+        uint32_t my_next = (uint32_t)group;    // ordinal (in this CTA's chunk stream) of my group's next chunk
+        uint32_t c0 = 0;                       // ordinal of the current work item's first chunk
+        uint32_t slot = (uint32_t)group, phase = 0;   // ring position of my_next (G <= S)
+        uint32_t witer = 0;
         for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++witer) {
-            const int tile = w / P.splits, split = w - tile * P.splits;
-            const int lo = split * per_split, hi = min(lo + per_split, P.chunks_total);
+            const int tile = w / P.splits;
             const int64_t row0 = (int64_t)tile * BM;
-            const uint32_t ibuf = witer & 1u;
-            if (group == 0) cp_async_wait_dyn((int)min(since_prefetch, lag));   // this tile's rulebook rows landed
-            since_prefetch = 0;
-            asm volatile("bar.sync 1, 256;" ::: "memory");                       // ... and are visible to group 1
-            const int wn = w + gridDim.x;
-            if (group == 0 && wn < num_work) prefetch_idx(wn / P.splits, ibuf ^ 1u);
-            int ord = 0;
-            for (int s = 0; s < d.n_seg; ++s) {
-                const tl_conv_seg& sg = d.seg[s];
-                const uint32_t mask = seg_mask(sg, tile);
-                const int kblocks = sg.c_in / BK;
-                const float* wseg = sg.weight + (int64_t)brow * sg.c_in + chunk * 4;
-                const int64_t wrow_stride = (int64_t)16 * sg.c_in;
-                for (int k = 0; k < sg.n_off; ++k, ord += kblocks) {
-                    if (ord >= hi) break;
-                    if (ord + kblocks <= lo || !((mask >> k) & 1u)) continue;
-                    const int kb_lo = max(lo - ord, 0), kb_hi = min(hi - ord, kblocks);
-                    // which of this offset's chunks does my group own?
-                    const uint32_t first_owned = (cidx & 1u) == (uint32_t)group ? 0u : 1u;
-                    if ((int)first_owned < kb_hi - kb_lo) {
-                        int my_row;
-                        if (sg.index) my_row = ld_shared_i32(L.idx(ibuf, P.idx_base[s] + k, col));
-                        else my_row = (row0 + col) < d.n_out ? (int)(row0 + col) : -1;
-                        const float* rp[8];
-                        uint32_t vmask = 0;
+            const uint32_t buf = witer & 1u;
+            mbar_wait(L.wfull(buf), (witer >> 1) & 1u);
+            const uint32_t n = ld_shared_u32(L.count(buf));
+            uint32_t prev_sk = 0xffffffffu;
+            const float* rp[8];
+            uint32_t vmask = 0;
+            const float* wk = nullptr;
+            int64_t wrow_stride = 0;
+            while (my_next < c0 + n) {
+                const uint32_t e = ld_shared_u32(L.list(buf, (int)(my_next - c0)));
+                const int kb = (int)(e & 7u);
+                if ((e >> 3) != prev_sk) {     // new (segment, offset): row pointers of my 8 (row, 16 B chunk) slots
+                    prev_sk = e >> 3;
+                    const int s = (int)(e >> 8), k = (int)((e >> 3) & 31u);
+                    const tl_conv_seg& sg = d.seg[s];
+                    int my_row;
+                    if (sg.index) my_row = ld_shared_i32(L.idx(buf, P.idx_base[s] + k, col));
+                    else my_row = (row0 + col) < d.n_out ? (int)(row0 + col) : -1;
+                    vmask = 0;
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int r = __shfl_sync(0xffffffffu, my_row, i * 4 + sub);
-                            vmask |= (r >= 0 ? 1u : 0u) << i;
-                            rp[i] = sg.src + (int64_t)max(r, 0) * sg.src_stride + chunk * 4;
-                        }
-                        const float* wk = wseg + (int64_t)k * N * sg.c_in;
-                        for (int kb = kb_lo; kb < kb_hi; ++kb) {
-                            const bool mine = (cidx & 1u) == (uint32_t)group;
-                            if (mine) {
-                                mbar_wait(L.empty(slot), phase ^ 1u);
-                                const uint32_t a_st = L.a(slot), b_st = L.b(slot) + b_off0;
-#pragma unroll
-                                for (int i = 0; i < 8; ++i)
-                                    cp_async16(a_st + a_off[i], rp[i] + kb * BK, ((vmask >> i) & 1u) ? 16u : 0u);
-                                const float* wp = wk + kb * BK;
-                                for (int j = 0; j < nb; ++j) cp_async16(b_st + j * 2048, wp + j * wrow_stride, 16u);
-                                cp_async_commit();
-                                ++own_issued;
-                                ++since_prefetch;
-                                if (own_issued - own_pub > lag) {
-                                    cp_async_wait_dyn((int)lag);
-                                    fence_proxy_async();
-                                    mbar_arrive(L.full(pub_slot));
-                                    ++own_pub;
-                                    pub_slot += 2;
-                                    if (pub_slot >= S) pub_slot -= S;
-                                }
-                            }
-                            ++cidx;
-                            if (++slot == S) slot = 0, phase ^= 1u;
-                        }
-                    } else {   // nothing owned here: just advance the stream position
-                        const int cnt = kb_hi - kb_lo;
-                        for (int c = 0; c < cnt; ++c) {
-                            ++cidx;
-                            if (++slot == S) slot = 0, phase ^= 1u;
-                        }
+                    for (int i = 0; i < 8; ++i) {
+                        const int r = __shfl_sync(0xffffffffu, my_row, i * 4 + sub);
+                        vmask |= (r >= 0 ? 1u : 0u) << i;
+                        rp[i] = sg.src + (int64_t)max(r, 0) * sg.src_stride + chunk * 4;
                     }
+                    wk = sg.weight + ((int64_t)k * N + brow) * sg.c_in + chunk * 4;
+                    wrow_stride = (int64_t)16 * sg.c_in;
                 }
+                mbar_wait(L.empty(slot), phase ^ 1u);
+                const uint32_t a_st = L.a(slot), b_st = L.b(slot) + b_off0;
+                if (P.debug & 2) {
+                } else if (P.use_cg) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        cp_async16_cg(a_st + a_off[i], rp[i] + kb * BK, ((vmask >> i) & 1u) ? 16u : 0u);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        cp_async16(a_st + a_off[i], rp[i] + kb * BK, ((vmask >> i) & 1u) ? 16u : 0u);
+                }
+                if (!(P.debug & 8)) {
+                    const float* wp = wk + kb * BK;
+                    for (int j = 0; j < nb; ++j) cp_async16(b_st + j * 2048, wp + j * wrow_stride, 16u);
+                }
+                cp_async_mbar_arrive_noinc(L.full(slot));
+                my_next += G;
+                slot += G;
+                if (slot >= S) slot -= S, phase ^= 1u;
             }
+            c0 += n;
+            mbar_arrive(L.wempty(buf));
         }
-        cp_async_wait_dyn(0);
-        fence_proxy_async();
-        for (; own_pub < own_issued; ++own_pub) {
-            mbar_arrive(L.full(pub_slot));
-            pub_slot += 2;
-            if (pub_slot >= S) pub_slot -= S;
-        }
-    } else if (warp < kProducerWarps + 4) {
+    } else if (warp >= kFirstEpilogueWarp && warp < kFirstEpilogueWarp + 4) {
         // ===================== epilogue: TMEM -> registers -> global ================================
-        const int ew = warp - kProducerWarps;  // == warp % 4: the TMEM lane quarter this warp may touch
+        const int ew = warp - kFirstEpilogueWarp;  // == warp % 4: the TMEM lane quarter this warp may touch
         uint32_t titer = 0;
         for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++titer) {
-            const int tile = w / P.splits, split = w - tile * P.splits;
+            const int tile = w / P.splits;
             const uint32_t buf = titer & 1u;
-            bool any = false;
-            for_each_chunk(d, tile, split * per_split, min((split + 1) * per_split, P.chunks_total),
-                           [&](int, int, int, bool) { any = true; });
+            mbar_wait(L.wfull(buf), (titer >> 1) & 1u);
+            const bool any = ld_shared_u32(L.count(buf)) != 0u;
+            mbar_arrive(L.wempty(buf));
             mbar_wait(L.tfull(buf), (titer >> 1) & 1u);
             tc_fence_after();
             const int64_t row = (int64_t)tile * BM + ew * 32 + lane;
-            const bool live = row < d.n_out;
+            const bool live = row < d.n_out && !(P.debug & 4);
             const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + buf * P.buf_cols;
             if (P.splits > 1) {
                 if (any) {
                     for (int c0 = 0; c0 < N; c0 += 32) {
                         uint32_t acc[32];
                         tmem_ld32(taddr + c0, acc);
+                        for (int way = 1; way < P.acc_ways; ++way) {
+                            uint32_t more[32];
+                            tmem_ld32(taddr + way * P.acc_cols + c0, more);
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(__uint_as_float(acc[j]) + __uint_as_float(more[j]));
+                        }
                         if (live) {
                             float* wp = P.splitk_ws + row * N + c0;
 #pragma unroll
@@ -389,8 +419,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const tl_conv_desc d, c
             } else {
                 for (int c0 = 0; c0 < N; c0 += 32) {
                     uint32_t acc[32];
-                    if (any) tmem_ld32(taddr + c0, acc);
-                    else
+                    if (any) {
+                        tmem_ld32(taddr + c0, acc);
+                        for (int way = 1; way < P.acc_ways; ++way) {
+                            uint32_t more[32];
+                            tmem_ld32(taddr + way * P.acc_cols + c0, more);
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(__uint_as_float(acc[j]) + __uint_as_float(more[j]));
+                        }
+                    } else
 #pragma unroll
                         for (int j = 0; j < 32; ++j) acc[j] = 0u;
                     if (live) {
@@ -434,34 +471,40 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const tl_conv_desc d, c
             tc_fence_before();
             mbar_arrive(L.tempty(buf));
         }
-    } else {
+    } else if (warp == kMmaWarp) {
         // ===================== MMA issuer (one elected thread) ======================================
         if (lane == 0) {
             const uint32_t idesc = make_idesc_tf32(N);
-            uint32_t it = 0, titer = 0;
+            const uint64_t adesc0 = make_smem_desc(L.a0), bdesc0 = make_smem_desc(L.b0);
+            const uint32_t a_step = A_STAGE_BYTES >> 4, b_step = L.b_stage_bytes >> 4;
+            const uint32_t wmask = (uint32_t)(P.acc_ways - 1);
+            uint32_t slot = 0, phase = 0, titer = 0;
             for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++titer) {
-                const int tile = w / P.splits, split = w - tile * P.splits;
                 const uint32_t buf = titer & 1u;
+                mbar_wait(L.wfull(buf), (titer >> 1) & 1u);
+                const uint32_t n = ld_shared_u32(L.count(buf));
+                mbar_arrive(L.wempty(buf));
                 mbar_wait(L.tempty(buf), ((titer >> 1) & 1u) ^ 1u);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + buf * P.buf_cols;
-                uint32_t first = 1;
-                for_each_chunk(d, tile, split * per_split, min((split + 1) * per_split, P.chunks_total),
-                               [&](int, int, int, bool) {
-                    const uint32_t slot = it % S;
-                    mbar_wait(L.full(slot), (it / S) & 1u);
+                for (uint32_t c = 0; c < n; ++c) {
+                    mbar_wait(L.full(slot), phase);
                     tc_fence_after();
-                    const uint64_t adesc = make_smem_desc(L.a(slot));
-                    const uint64_t bdesc = make_smem_desc(L.b(slot));
+                    const uint64_t adesc = adesc0 + (uint64_t)(slot * a_step);
+                    const uint64_t bdesc = bdesc0 + (uint64_t)(slot * b_step);
+                    if (!(P.debug & 1)) {
 #pragma unroll
-                    for (int kk = 0; kk < BK / 8; ++kk)  // UMMA_K = 8 for tf32: advance 32 B inside the swizzle atom
-                        umma_tf32(tmem_d, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc,
-                                  (first && kk == 0) ? 0u : 1u);
-                    first = 0;
+                        for (int kk = 0; kk < BK / 8; ++kk) {  // UMMA_K = 8 for tf32: advance 32 B inside the swizzle atom
+                            // K-step kk accumulates into its own TMEM tile kk % ways (the epilogue adds the tiles up)
+                            const uint32_t way = (uint32_t)kk & wmask;
+                            umma_tf32(tmem_d + way * P.acc_cols, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2),
+                                      idesc, (c == 0 && (uint32_t)kk <= wmask) ? 0u : 1u);
+                        }
+                    }
                     umma_commit(L.empty(slot));
-                    ++it;
-                });
-                if (first) mbar_arrive(L.tfull(buf));  // no pair in this work item: nothing to accumulate
+                    if (++slot == S) slot = 0, phase ^= 1u;
+                }
+                if (n == 0) mbar_arrive(L.tfull(buf));  // no pair in this work item: nothing to accumulate
                 else umma_commit(L.tfull(buf));
             }
         }
@@ -580,15 +623,19 @@ int conv_fwd_tc(const tl_conv_desc& d, cudaStream_t stream) {
         TL_CUDA_CHECK(cudaGetDevice(&dev));
         TL_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
         TL_CUDA_CHECK(cudaFuncSetAttribute(tc::k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        smem_budget = env_int("TL_TC_SMEM_KB", 128) * 1024;   // keep the rest of the 228 KB as L1 for the gather
+        smem_budget = env_int("TL_TC_SMEM_KB", 200) * 1024;   // keep the rest of the 228 KB as L1 for the gather
         split_target = env_int("TL_TC_SPLIT_WAVES", 2);        // split-K until work items >= waves * SMs
         TL_CUDA_CHECK(cudaFuncSetAttribute(tc::k_conv_tc, cudaFuncAttributePreferredSharedMemoryCarveout,
                                            env_int("TL_TC_CARVEOUT", 58)));
     }
     const int n = d.c_out;
     tc::Launch P;
-    P.buf_cols = 32;
-    while (P.buf_cols < n) P.buf_cols <<= 1;
+    P.acc_cols = 32;
+    while (P.acc_cols < n) P.acc_cols <<= 1;
+    P.debug = env_int("TL_TC_DEBUG", 0);
+    P.acc_ways = env_int("TL_TC_WAYS", 4);
+    while (P.acc_ways > 1 && 2 * P.acc_ways * P.acc_cols > 512) P.acc_ways >>= 1;
+    P.buf_cols = P.acc_ways * P.acc_cols;
     P.tmem_cols = 2 * P.buf_cols;  // <= 512
     const size_t stage = tc::A_STAGE_BYTES + (size_t)n * 128;
     int stages = (int)((smem_budget - 2048 - 2 * tc::IDX_BUF_BYTES) / stage);
@@ -598,8 +645,12 @@ int conv_fwd_tc(const tl_conv_desc& d, cudaStream_t stream) {
     P.stages = stages;
     // two producer groups alternate chunks, each keeps `lag` of its own cp.async groups in flight before publishing
     // the oldest; 2*lag < stages keeps the ring deadlock-free (a group can always publish what the MMA waits for)
-    P.lag = (stages - 1) / 2;
+    int groups = env_int("TL_TC_GROUPS", tc::kMaxGroups);
+    while (groups > 1 && (groups > stages || groups > tc::kMaxGroups)) groups >>= 1;
+    P.groups = groups;
+    P.lag = (stages - 1) / groups;     // G * lag < stages: the ring cannot deadlock
     if (P.lag < 1) P.lag = 1;
+    P.use_cg = env_int("TL_TC_CG", 1);
     const size_t smem = tc::smem_bytes(n, stages);
     P.num_tiles = (d.n_out + tc::BM - 1) / tc::BM;
     P.chunks_total = 0;
@@ -616,7 +667,9 @@ int conv_fwd_tc(const tl_conv_desc& d, cudaStream_t stream) {
         if (alias >= 0) P.idx_base[s] = P.idx_base[alias];
         else P.idx_base[s] = idx_rows, P.idx_owner[s] = 1, idx_rows += d.seg[s].n_off;
     }
-    if (idx_rows > tc::IDX_ROWS) return conv_fwd_simt_fallback_note(d, stream);
+    if (idx_rows > tc::IDX_ROWS || P.chunks_total > tc::MAX_CHUNKS) return conv_fwd_simt_fallback_note(d, stream);
+    for (int s = 0; s < d.n_seg; ++s)
+        TL_REQUIRE(!d.seg[s].index || d.seg[s].index_stride % 4 == 0, "tl_conv_fwd(tf32): index_stride must be a multiple of 4");
     P.splits = 1;
     P.splitk_ws = nullptr;
     if (d.splitk_ws && P.num_tiles < split_target * num_sms) {
