@@ -1,0 +1,46 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic: tile sharding and the variable-length all-gather."""
+import os
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from treelearn_b200.dist import allgather_rows, shard_indices
+
+
+def test_shard_indices_is_a_balanced_partition():
+    w = [10, 1, 7, 7, 3, 9, 2, 8]
+    parts = [shard_indices(w, r, 3) for r in range(3)]
+    assert sorted(sum(parts, [])) == list(range(len(w)))
+    loads = [sum(w[i] for i in p) for p in parts]
+    assert max(loads) - min(loads) <= max(w)
+    assert shard_indices(w, 0, 1) == list(range(len(w)))
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    n = 3 + 4 * rank                      # ragged: rank 0 -> 3 rows, rank 1 -> 7 rows
+    t = torch.arange(n * 2, dtype=torch.float32).reshape(n, 2) + 100 * rank
+    out = allgather_rows(t)
+    empty = allgather_rows(torch.zeros((0, 2)) if rank == 0 else t)     # an empty contribution
+    q.put((rank, out.tolist(), empty.shape[0]))
+    dist.destroy_process_group()
+
+
+def test_allgather_rows_gloo_world2():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    expect = (torch.arange(6, dtype=torch.float32).reshape(3, 2).tolist()
+              + (torch.arange(14, dtype=torch.float32).reshape(7, 2) + 100).tolist())
+    for rank, out, n_empty in res:
+        assert out == expect            # identical on both ranks, rank order preserved
+        assert n_empty == 7

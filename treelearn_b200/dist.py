@@ -1,0 +1,68 @@
+"""Multi-GPU plumbing for the two places the path shards.  One process per GPU, torch.distributed.
+
+Inference: tiles are independent units (tree_learn/util/pipeline.py:83-103) => tile i goes to one rank (longest-
+processing-time-first by point count), every rank crops its tiles to the inner square on the device, ONE variable-size
+all-gather exchanges the inner rows, and the overlap merge (`ensemble`) + clustering run replicated on the merged
+plot (the reference clusters the whole plot at once, tools/pipeline/pipeline.py:89-94).
+The reference has no distributed code at all; these helpers are new.  They work with the nccl (GPU) and gloo (CPU
+tests of the host logic) backends.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_indices(weights, rank, world):
+    """Greedy longest-processing-time-first partition of items (tiles) by weight; returns this rank's item indices
+    in ascending order.  Deterministic: every rank computes the same assignment."""
+    order = sorted(range(len(weights)), key=lambda i: (-float(weights[i]), i))
+    load = [0.0] * world
+    mine = []
+    for i in order:
+        r = min(range(world), key=lambda j: (load[j], j))
+        load[r] += float(weights[i])
+        if r == rank:
+            mine.append(i)
+    return sorted(mine)
+
+
+def allgather_rows(t, group=None):
+    """Variable-length all-gather along dim 0: every rank passes [n_r, ...] and gets cat over ranks (rank order)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return t
+    world = dist.get_world_size(group)
+    n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(s.item()) for s in sizes]
+    m = max(sizes)
+    pad = torch.zeros((m,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    pad[:t.shape[0]] = t
+    out = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(out, pad, group=group)
+    return torch.cat([o[:s] for o, s in zip(out, sizes)], dim=0)
+
+
+def segment_plot(model, tiles, grouping_cfg, group=None):
+    """Whole-plot inference (BASELINE.json config 4): `tiles` is the same list of host batch dicts on every rank.
+    Returns (merged coords [P,3], instance labels [P]) as CUDA tensors, identical on every rank."""
+    from . import pipeline
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    mine = shard_indices([t['coords'].shape[0] for t in tiles], rank, world)
+    rows = []
+    dev = torch.device('cuda', torch.cuda.current_device())
+    with torch.no_grad():
+        model.eval()
+        for i in mine:
+            b = tiles[i]
+            out = model(b, return_loss=False)
+            inner = b['masks_inner'].to(dev)
+            xyz = (b['coords'] + b['centers']).to(dev)[inner]
+            rows.append(torch.cat([xyz, out['semantic_prediction_logits'][inner], out['offset_predictions'][inner],
+                                   b['input_feats'].to(dev)[inner][:, -1:]], dim=1))
+    local = torch.cat(rows) if rows else torch.zeros((0, 9), device=dev)
+    allrows = allgather_rows(local.contiguous(), group)          # the one collective of the inference path
+    coords, vals = pipeline.ensemble_cuda(allrows[:, :3].contiguous(), allrows[:, 3:].contiguous())
+    labels, n_clusters = pipeline.instances_cuda(coords, vals[:, 2:5].contiguous(), vals[:, 0:2].contiguous(),
+                                                 vals[:, 5].contiguous(), grouping_cfg)
+    return coords, labels, n_clusters

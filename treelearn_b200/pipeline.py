@@ -60,6 +60,25 @@ def get_pointwise_preds(model, dataloader, config, logger=None):
             cat['in_feats'])
 
 
+def ensemble_cuda(xyz, vals):
+    """Device-resident overlap merge: xyz [n,3] f32, vals [n,V] f32 (CUDA) -> (coords [g,3], means [g,V]) sorted by
+    the rounded (x,y,z) key; same arithmetic as `ensemble`."""
+    lib = _lib.load()
+    n, nv = int(xyz.shape[0]), int(vals.shape[1])
+    dev = xyz.device
+    if n == 0:
+        return xyz.new_zeros((0, 3)), vals.new_zeros((0, nv))
+    out_xyz = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    out_vals = torch.empty((n, nv), dtype=torch.float32, device=dev)
+    gid = torch.empty(n, dtype=torch.int32, device=dev)
+    ng = C.c_int64(0)
+    wsb = lib.tl_merge_workspace_bytes(n)
+    ws = _ws(wsb, dev)
+    check(lib.tl_merge_groupby_mean(ptr(xyz.contiguous().float()), ptr(vals.contiguous().float()), n, nv, ptr(out_xyz),
+                                    ptr(out_vals), ptr(gid), C.byref(ng), ptr(ws), wsb, stream_ptr()))
+    return out_xyz[:ng.value], out_vals[:ng.value]
+
+
 def ensemble(coords, semantic_scores, semantic_labels, offset_predictions, offset_labels, instance_labels, feats,
              input_feats):
     """Overlap merge: group rows by round(coords, 2), mean of every column, sorted by (x,y,z)."""
