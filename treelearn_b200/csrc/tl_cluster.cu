@@ -281,41 +281,55 @@ struct TopK {
     }
 };
 
-__global__ void k_knn_vote(const float* __restrict__ query, int64_t nq, const uint64_t* __restrict__ tkeys,
-                           const int* __restrict__ tvals, uint64_t mask, const int* __restrict__ seg_start,
-                           const int* __restrict__ sidx, const float* __restrict__ spts,
-                           const int64_t* __restrict__ ref_labels, int64_t n_ref, double cell, int k,
-                           int64_t* __restrict__ out) {
+struct GridView {
+    const uint64_t* tkeys;
+    const int* tvals;
+    uint64_t mask;
+    const int* seg_start;
+    const int* sidx;
+    const float* spts;
+    double cell;
+    int max_ring;
+};
+
+// Multi-resolution search: level 0 has small cells (dense tree-base blobs after the offset shift), coarser levels catch
+// sparse neighbourhoods without probing hundreds of empty cells; exact scan of all references as the last resort.
+// A level's result is final once the k-th distance is within the radius that level has provably covered.
+__global__ void k_knn_vote(const float* __restrict__ query, int64_t nq, GridView g0, GridView g1, GridView g2,
+                           const int64_t* __restrict__ ref_labels, int64_t n_ref, int k, int64_t* __restrict__ out) {
     int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (q >= nq) return;
     const double x = query[q * 3], y = query[q * 3 + 1], z = query[q * 3 + 2];
-    const int64_t cx = (int64_t)floor(x / cell), cy = (int64_t)floor(y / cell), cz = (int64_t)floor(z / cell);
     TopK top;
     bool done = false;
-    for (int ring = 1; ring <= kMaxRing && !done; ++ring) {
-        top.init(k);
-        for (int dx = -ring; dx <= ring; ++dx)
-            for (int dy = -ring; dy <= ring; ++dy)
-                for (int dz = -ring; dz <= ring; ++dz) {
-                    const int seg = hash_find(tkeys, tvals, mask, cell_key3(cx + dx, cy + dy, cz + dz));
-                    if (seg < 0) continue;
-                    for (int j = seg_start[seg]; j < seg_start[seg + 1]; ++j) {
-                        const double ax = x - (double)spts[j * 3], ay = y - (double)spts[j * 3 + 1],
-                                     az = z - (double)spts[j * 3 + 2];
-                        const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)), __dmul_rn(az, az));
-                        top.push(d2, ref_labels[sidx[j]], sidx[j]);
+    for (int level = 0; level < 3 && !done; ++level) {
+        const GridView& g = level == 0 ? g0 : (level == 1 ? g1 : g2);
+        const int64_t cx = (int64_t)floor(x / g.cell), cy = (int64_t)floor(y / g.cell), cz = (int64_t)floor(z / g.cell);
+        for (int ring = 1; ring <= g.max_ring && !done; ++ring) {
+            top.init(k);
+            for (int dx = -ring; dx <= ring; ++dx)
+                for (int dy = -ring; dy <= ring; ++dy)
+                    for (int dz = -ring; dz <= ring; ++dz) {
+                        const int seg = hash_find(g.tkeys, g.tvals, g.mask, cell_key3(cx + dx, cy + dy, cz + dz));
+                        if (seg < 0) continue;
+                        for (int j = g.seg_start[seg]; j < g.seg_start[seg + 1]; ++j) {
+                            const double ax = x - (double)g.spts[j * 3], ay = y - (double)g.spts[j * 3 + 1],
+                                         az = z - (double)g.spts[j * 3 + 2];
+                            const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)), __dmul_rn(az, az));
+                            top.push(d2, ref_labels[g.sidx[j]], g.sidx[j]);
+                        }
                     }
-                }
-        // every reference closer than ring*cell (minus the query's offset inside its cell, bounded by 0) was seen
-        const double safe = (double)ring * cell;
-        done = top.d[k - 1] <= safe * safe;
+            // every reference closer than ring*cell was seen (the query lies inside the centre cell)
+            const double safe = (double)ring * g.cell;
+            done = top.d[k - 1] <= safe * safe;
+        }
     }
-    if (!done) {  // sparse neighbourhood: exact scan of all references (rare)
+    if (!done) {  // farther than every grid reaches: exact scan of all references (rare)
         top.init(k);
         for (int64_t j = 0; j < n_ref; ++j) {
-            const double ax = x - (double)spts[j * 3], ay = y - (double)spts[j * 3 + 1], az = z - (double)spts[j * 3 + 2];
+            const double ax = x - (double)g0.spts[j * 3], ay = y - (double)g0.spts[j * 3 + 1], az = z - (double)g0.spts[j * 3 + 2];
             const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)), __dmul_rn(az, az));
-            top.push(d2, ref_labels[sidx[j]], sidx[j]);
+            top.push(d2, ref_labels[g0.sidx[j]], g0.sidx[j]);
         }
     }
     out[q] = top.vote();
@@ -422,7 +436,7 @@ int tl_cluster_radius_cc(const float* points_xy, int64_t n, double radius, int64
 size_t tl_knn_workspace_bytes(int64_t n_ref, int64_t n_query) {
     (void)n_query;
     if (n_ref <= 0) return 256;
-    return grid_bytes(n_ref) + 1024;
+    return 3 * (grid_bytes(n_ref) + 1024);
 }
 
 int tl_knn_vote(const float* ref_xyz, const int64_t* ref_labels, int64_t n_ref, const float* query_xyz, int64_t n_query,
@@ -432,14 +446,18 @@ int tl_knn_vote(const float* ref_xyz, const int64_t* ref_labels, int64_t n_ref, 
     TL_REQUIRE(k >= 1 && k <= kMaxK, "tl_knn_vote: k=%d (1..%d)", k, kMaxK);
     TL_REQUIRE(n_ref >= k && n_ref < (1ll << 31), "tl_knn_vote: n_ref=%lld must be >= k=%d", (long long)n_ref, k);
     Carver c(workspace, workspace_bytes);
-    CellGrid g;
-    TL_REQUIRE(carve_grid(c, n_ref, g), "tl_knn_vote: workspace too small");
-    const double cell = 0.25;
-    int rc = build_grid<3>(ref_xyz, n_ref, cell, g, stream);
-    if (rc != TL_OK) return rc;
-    k_knn_vote<<<(unsigned)((n_query + 127) / 128), 128, 0, stream>>>(query_xyz, n_query, g.tkeys, g.tvals, g.cap - 1,
-                                                                      g.seg_start, g.idx_out, g.spts, ref_labels, n_ref,
-                                                                      cell, k, out_labels);
+    const double cells[3] = {0.25, 1.0, 4.0};
+    const int rings[3] = {2, 3, 4};
+    GridView gv[3];
+    for (int l = 0; l < 3; ++l) {
+        CellGrid g;
+        TL_REQUIRE(carve_grid(c, n_ref, g), "tl_knn_vote: workspace too small");
+        int rc = build_grid<3>(ref_xyz, n_ref, cells[l], g, stream);
+        if (rc != TL_OK) return rc;
+        gv[l] = GridView{g.tkeys, g.tvals, g.cap - 1, g.seg_start, g.idx_out, g.spts, cells[l], rings[l]};
+    }
+    k_knn_vote<<<(unsigned)((n_query + 127) / 128), 128, 0, stream>>>(query_xyz, n_query, gv[0], gv[1], gv[2], ref_labels,
+                                                                      n_ref, k, out_labels);
     TL_LAUNCH_CHECK();
     return TL_OK;
 }
