@@ -165,7 +165,7 @@ def run_b200(args):
     peak, peak_src = peaks()
     achieved = conv_bytes / (conv_ms * 1e-3) / 1e9 if conv_ms > 0 else 0.0
     roofline = {'bound': 'hbm', 'kernel': 'k_conv_simt (segmented gather-GEMM sparse conv)' if args.mode == 'fp32'
-                else 'k_conv_tc (tcgen05 tf32 gather-GEMM sparse conv)',
+                else f'k_conv_tc (tcgen05 {args.mode} gather-GEMM sparse conv)',
                 'achieved': round(achieved, 1), 'peak': peak, 'unit': 'GB/s', 'frac': round(achieved / peak, 4),
                 'traffic': None, 'peak_source': peak_src, 'launches_per_step': per_step,
                 'kernel_ms_per_step': round(conv_ms / args.steps, 3),
@@ -182,7 +182,7 @@ def run_b200(args):
     line = {
         'metric': METRIC, 'value': round(value, 2), 'unit': 'Mvoxels/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': round(ms_res, 3), 'higher_is_better': True, 'scaling': 'weak',
-        'vs_baseline': None, 'dtype': 'f32' if args.mode == 'fp32' else 'tf32 (tcgen05 kind::tf32, fp32 accumulate; fp32 storage)', 'data': 'synthetic',
+        'vs_baseline': None, 'dtype': {'fp32': 'f32', 'tf32': 'tf32 (tcgen05 kind::tf32, fp32 accumulate; fp32 storage)', 'f16': 'f16 operands (tcgen05 kind::f16, fp32 accumulate, fp32 residual stream)'}[args.mode], 'data': 'synthetic',
         'config': {'workload': f'{args.workload}: one synthetic forest tile per GPU, {int(n_vox_total / world)} active '
                                f'0.1 m voxels, default 7-level 32-channel U-Net (random init, BN eval, randomised stats) '
                                f'+ DBSCAN-equivalent clustering + kNN assignment', 'spatial_shape': SPATIAL_SHAPE,
@@ -280,7 +280,7 @@ if __name__ == '__main__':
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='cfg2_2M')
-    ap.add_argument('--mode', default='tf32', choices=['fp32', 'tf32'])
+    ap.add_argument('--mode', default='tf32', choices=['fp32', 'tf32', 'f16'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     a = ap.parse_args()
     if a.impl == 'reference':

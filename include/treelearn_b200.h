@@ -71,7 +71,7 @@ int tl_subm_rulebook(const uint64_t* keys, int64_t n, const int32_t* spatial_sha
  *   acc[r,:] = sum_seg sum_k W_seg[k] . src_seg[index_seg[k][r], :]     (index NULL => identity, n_off==1)
  *   v = acc + residual[r,:]
  *   out_raw = v ; out_act1 = relu(scale1*v+shift1) ; out_act2 = relu(scale2*v+shift2)   (each optional)
- * weight layout: mode 0 (fp32 SIMT) [n_off][c_in][c_out]; mode 1 (tf32 tcgen05) [n_off][c_out][c_in]. */
+ * weight layout: mode 0 (fp32 SIMT) [n_off][c_in][c_out]; modes 1/2 (tcgen05 tf32 / f16) [n_off][c_out][c_in]. */
 typedef struct {
     const float* src;
     int64_t src_stride; /* floats per row */
@@ -102,12 +102,15 @@ typedef struct {
 
 #define TL_MODE_FP32 0
 #define TL_MODE_TF32 1
+#define TL_MODE_F16 2 /* tcgen05 kind::f16: segment sources, weights and the activated outputs (out_act1/2) are fp16;
+                         residual, out_raw and the accumulation stay fp32 */
 int tl_conv_fwd(const tl_conv_desc* desc, int32_t mode, void* stream);
 
 /* ---- voxel -> point gather + the two MLP heads: replaces `features[v2p_map]` and MLP forward
  *      (tree_learn/model/tree_learn.py:97-103, blocks.py:8-18).  BN(eval) is folded into w1/b1 by the host.
  * voxel_feats [M,C]; v2p [N]; per head h in {sem(2), off(3)}: w1 [C][C] (row = out), b1 [C], w2 [O][C], b2 [O]. */
-int tl_heads_fwd(const float* voxel_feats, const int64_t* v2p, int64_t n_points, int32_t channels,
+int tl_heads_fwd(const void* voxel_feats, int32_t feats_half /* 1: voxel_feats is fp16 (TL_MODE_F16 backbone) */,
+                 const int64_t* v2p, int64_t n_points, int32_t channels,
                  const float* sem_w1, const float* sem_b1, const float* sem_w2, const float* sem_b2,
                  const float* off_w1, const float* off_b1, const float* off_w2, const float* off_b2,
                  float* backbone_feats, float* sem_logits, float* offsets, void* stream);

@@ -344,3 +344,54 @@ def test_tc_matches_fp32_path_on_larger_tile():
     print('tf32 vs fp32 offsets', err)
     assert err < 1e-3
     assert (outs['tf32']['semantic_prediction_logits'] - outs['fp32']['semantic_prediction_logits']).abs().max() < 2e-3
+
+
+# ---- tcgen05 / fp16-operand path -------------------------------------------------------------------
+@pytest.mark.parametrize('ci,co', [(32, 32), (64, 32), (96, 96), (224, 224)])
+def test_f16_subm_conv_parity(ci, co):
+    batch = synth.make_batch([synth.synth_forest(edge=5.0, n_trees=2, seed=9, ground_density=200.0)])
+    (vf, vc, keys, v2p), _ = _voxelize_both(batch)
+    lv = sparse.build_levels(keys, vc, [500, 500, 1000], 1)[0]
+    g = torch.Generator().manual_seed(ci * 1000 + co + 7)
+    x = torch.randn((lv.n, ci), generator=g).half()
+    w = (torch.randn((co, 3, 3, 3, ci), generator=g) / (27 * ci) ** 0.5).half()
+    res = torch.randn((lv.n, co), generator=g)
+    s, t = torch.rand(co, generator=g) + 0.5, torch.randn(co, generator=g)
+    ref = model_ref._subm(x.float(), sp.subm_neighbour_table(vc.cpu().numpy(), [500, 500, 1000]), w.float()) + res
+    wp = w.reshape(co, 27, ci).permute(1, 0, 2).contiguous().cuda()
+    raw, act = sparse.conv([sparse.Seg(x.cuda(), wp, lv.nbr, lv.nbr_mask)], lv.n, co, _lib.MODE_F16,
+                           residual=res.cuda(), raw=True, act1=(s.cuda(), t.cuda()))
+    assert raw.dtype == torch.float32 and act.dtype == torch.float16
+    assert torch.allclose(raw.cpu(), ref, **TF32_EXACT_TOL)
+    assert torch.allclose(act.cpu().float(), torch.relu(ref * s + t), atol=3e-3, rtol=2e-3)   # + fp16 rounding of the store
+
+
+def test_f16_default_model_offsets_within_1e3_of_fp32_oracle():
+    batch = _tile('tiny')
+    sd = model_ref.make_state_dict(channels=32, num_blocks=7, seed=0)
+    net = TreeLearn(use_feats=False, use_coords=False, spatial_shape=[500, 500, 1000], mode='f16')
+    net.load_state_dict(sd)
+    net = net.cuda().eval()
+    with torch.no_grad():
+        mine = net(batch, return_loss=False)
+        ref = model_ref.forward_ref(sd, batch, spatial_shape=[500, 500, 1000])
+    err = (mine['offset_predictions'].cpu() - ref['offset_predictions']).abs().max().item()
+    print('f16 offset max err', err)
+    assert err < 1e-3
+    assert (mine['semantic_prediction_logits'].cpu() - ref['semantic_prediction_logits']).abs().max() < 2e-3
+    assert mine['backbone_feats'].dtype == torch.float32
+
+
+def test_f16_matches_fp32_path_on_larger_tile():
+    batch = _tile('small')
+    sd = model_ref.make_state_dict(channels=32, num_blocks=7, seed=1)
+    outs = {}
+    for mode in ('fp32', 'f16'):
+        net = TreeLearn(use_feats=False, use_coords=False, spatial_shape=[500, 500, 1000], mode=mode)
+        net.load_state_dict(sd)
+        net = net.cuda().eval()
+        with torch.no_grad():
+            outs[mode] = net(batch, return_loss=False)
+    err = (outs['f16']['offset_predictions'] - outs['fp32']['offset_predictions']).abs().max().item()
+    print('f16 vs fp32 offsets', err)
+    assert err < 1e-3

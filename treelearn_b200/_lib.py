@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, 'libtreelearn_b200.so')
 
 TL_MAX_SEG = 3
 TILE_ROWS = 128
-MODE_FP32, MODE_TF32 = 0, 1
+MODE_FP32, MODE_TF32, MODE_F16 = 0, 1, 2
 ERR_REACH_ZERO = -3
 
 
@@ -48,7 +48,7 @@ SIGNATURES = {
     'tl_rulebook_workspace_bytes': (_SZ, [_I64]),
     'tl_subm_rulebook': (C.c_int, [_P, _I64, _I32P, _P, _P, _P, _SZ, _P]),
     'tl_conv_fwd': (C.c_int, [C.POINTER(ConvDesc), _I32, _P]),
-    'tl_heads_fwd': (C.c_int, [_P, _P, _I64, _I32] + [_P] * 8 + [_P, _P, _P, _P]),
+    'tl_heads_fwd': (C.c_int, [_P, _I32, _P, _I64, _I32] + [_P] * 8 + [_P, _P, _P, _P]),
     'tl_merge_workspace_bytes': (_SZ, [_I64]),
     'tl_merge_groupby_mean': (C.c_int, [_P, _P, _I64, _I32, _P, _P, _P, _I64P, _P, _SZ, _P]),
     'tl_cluster_workspace_bytes': (_SZ, [_I64]),

@@ -3,6 +3,8 @@
 // One CTA = TM output rows x all C_out columns; per kernel offset the gathered input rows and
 // the offset's weight slab are staged in shared memory in 32-channel chunks; each thread keeps an
 // RPT x NCOL register tile (rows warp-striped, columns lane-striped => coalesced epilogue).
+#include <cuda_fp16.h>
+
 #include "tl_common.cuh"
 
 namespace tl {
@@ -120,13 +122,13 @@ int conv_fwd_simt(const tl_conv_desc& d, cudaStream_t stream) {
     return TL_ERR_UNSUPPORTED;
 }
 
-int conv_fwd_tc(const tl_conv_desc& d, cudaStream_t stream);  // tl_conv_tc.cu
+int conv_fwd_tc(const tl_conv_desc& d, cudaStream_t stream, bool half);  // tl_conv_tc.cu
 
 // ------------------------------------------------------------------------------------------------
 // voxel -> point gather + both MLP heads, one thread per point, weights broadcast from smem
 // ------------------------------------------------------------------------------------------------
-template <int C>
-__global__ void __launch_bounds__(128) k_heads(const float* __restrict__ vfeat, const int64_t* __restrict__ v2p,
+template <int C, bool HALF_IN>
+__global__ void __launch_bounds__(128) k_heads(const void* __restrict__ vfeat_, const int64_t* __restrict__ v2p,
                                                int64_t n, const float* __restrict__ sw1, const float* __restrict__ sb1,
                                                const float* __restrict__ sw2, const float* __restrict__ sb2,
                                                const float* __restrict__ ow1, const float* __restrict__ ob1,
@@ -155,14 +157,26 @@ __global__ void __launch_bounds__(128) k_heads(const float* __restrict__ vfeat, 
     __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float4* src = reinterpret_cast<const float4*>(vfeat + v2p[i] * C);
     float4* dst = reinterpret_cast<float4*>(feats + i * C);
     float x[C];
+    if (HALF_IN) {
+        const uint2* src = reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(vfeat_) + v2p[i] * C);
 #pragma unroll
-    for (int c = 0; c < C / 4; ++c) {
-        const float4 v = __ldg(src + c);
-        dst[c] = v;
-        x[4 * c] = v.x, x[4 * c + 1] = v.y, x[4 * c + 2] = v.z, x[4 * c + 3] = v.w;
+        for (int c = 0; c < C / 4; ++c) {
+            const uint2 raw = __ldg(src + c);
+            const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+            const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+            x[4 * c] = lo.x, x[4 * c + 1] = lo.y, x[4 * c + 2] = hi.x, x[4 * c + 3] = hi.y;
+            dst[c] = make_float4(lo.x, lo.y, hi.x, hi.y);
+        }
+    } else {
+        const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(vfeat_) + v2p[i] * C);
+#pragma unroll
+        for (int c = 0; c < C / 4; ++c) {
+            const float4 v = __ldg(src + c);
+            dst[c] = v;
+            x[4 * c] = v.x, x[4 * c + 1] = v.y, x[4 * c + 2] = v.z, x[4 * c + 3] = v.w;
+        }
     }
     float y[5];
 #pragma unroll
@@ -223,21 +237,26 @@ int tl_conv_fwd(const tl_conv_desc* desc, int32_t mode, void* stream_) {
     TL_REQUIRE((!d.out_act1 || (d.scale1 && d.shift1)) && (!d.out_act2 || (d.scale2 && d.shift2)),
                "tl_conv_fwd: activation output without scale/shift");
     if (mode == TL_MODE_FP32) return conv_fwd_simt(d, stream);
-    if (mode == TL_MODE_TF32) return conv_fwd_tc(d, stream);
+    if (mode == TL_MODE_TF32) return conv_fwd_tc(d, stream, false);
+    if (mode == TL_MODE_F16) return conv_fwd_tc(d, stream, true);
     set_error("tl_conv_fwd: unknown mode %d", mode);
     return TL_ERR_ARG;
 }
 
-int tl_heads_fwd(const float* voxel_feats, const int64_t* v2p, int64_t n, int32_t channels, const float* sem_w1,
+int tl_heads_fwd(const void* voxel_feats, int32_t feats_half, const int64_t* v2p, int64_t n, int32_t channels, const float* sem_w1,
                  const float* sem_b1, const float* sem_w2, const float* sem_b2, const float* off_w1,
                  const float* off_b1, const float* off_w2, const float* off_b2, float* backbone_feats,
                  float* sem_logits, float* offsets, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (n == 0) return TL_OK;
     const unsigned grid = (unsigned)((n + 127) / 128);
-#define TL_HEADS(C)                                                                                              \
-    k_heads<C><<<grid, 128, 0, stream>>>(voxel_feats, v2p, n, sem_w1, sem_b1, sem_w2, sem_b2, off_w1, off_b1,    \
-                                          off_w2, off_b2, backbone_feats, sem_logits, offsets)
+#define TL_HEADS(C)                                                                                                 \
+    if (feats_half)                                                                                                 \
+        k_heads<C, true><<<grid, 128, 0, stream>>>(voxel_feats, v2p, n, sem_w1, sem_b1, sem_w2, sem_b2, off_w1,     \
+                                                    off_b1, off_w2, off_b2, backbone_feats, sem_logits, offsets);   \
+    else                                                                                                            \
+        k_heads<C, false><<<grid, 128, 0, stream>>>(voxel_feats, v2p, n, sem_w1, sem_b1, sem_w2, sem_b2, off_w1,    \
+                                                     off_b1, off_w2, off_b2, backbone_feats, sem_logits, offsets)
     switch (channels) {
         case 8: TL_HEADS(8); break;
         case 16: TL_HEADS(16); break;

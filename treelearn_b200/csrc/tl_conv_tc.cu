@@ -18,6 +18,7 @@
 // Shared memory is kept near 128 KB so that ~96 KB of L1 remains: the ~14x re-read of neighbour rows inside a
 // Morton-ordered tile is served by L1, not L2.
 // Weights arrive pre-rounded (RN) to TF32, layout [n_off][C_out][C_in] (K-major B operand).
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "tl_common.cuh"
@@ -26,9 +27,9 @@ namespace tl {
 namespace tc {
 
 constexpr int BM = 128;          // rows per tile == TMEM lanes
-constexpr int BK = 32;           // fp32 elements per K block == one 128 B swizzle row
+constexpr int BK = 32;           // channels per K block: one swizzle row of 128 B (fp32/TF32 operands) or 64 B (fp16)
 constexpr int MAX_STAGES = 12;
-constexpr int A_STAGE_BYTES = BM * 128;
+constexpr int A_STAGE_BYTES = BM * 128;   // fp32 operands (largest case; used for sizing)
 constexpr int kMaxGroups = 4;            // producer groups of four warps; group g fills the chunks with ordinal % G == g
 constexpr int kProducerWarps = 4 * kMaxGroups;
 constexpr int kProducerThreads = 128;    // arrivals per stage (one group)
@@ -105,18 +106,20 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 //   [0,14) start address >> 4 | [16,30) LBO >> 4 (ignored for swizzled K-major, set 1) | [32,46) SBO >> 4 (8 rows
 //   x 128 B = 1024) | [46,48) version = 1 (sm100) | [49,52) base offset = 0 (1024 B aligned stages) |
 //   [61,64) layout = 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+// row_bytes 128 -> SWIZZLE_128B (layout 2, SBO 1024); row_bytes 64 -> SWIZZLE_64B (layout 4, SBO 512)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, int row_bytes) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
     d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)((8 * row_bytes) >> 4) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= (uint64_t)(row_bytes == 128 ? 2 : 4) << 61;
     return d;
 }
 // cute::UMMA::InstrDescriptor: c_format F32 (1) @4, a/b format TF32 (2) @7/@10, K-major both, N>>3 @17, M>>4 @24
-__device__ __forceinline__ uint32_t make_idesc_tf32(int n) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+__device__ __forceinline__ uint32_t make_idesc(int n, bool half) {   // a/b format: 2 = TF32, 0 = F16
+    const uint32_t fmt = half ? 0u : 2u;
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
@@ -125,6 +128,17 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
         ".reg .pred p;\n"
         "setp.ne.b32 p, %4, 0;\n"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
         "}\n" ::"r"(tmem_d),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
@@ -151,6 +165,35 @@ __device__ __forceinline__ float round_tf32(float v) {
     return __uint_as_float(r);
 }
 
+// relu(scale*v+shift) of 32 consecutive columns -> the consumer's operand format: TF32-rounded fp32 or fp16
+template <int EB>
+__device__ __forceinline__ void store_act32(void* out, int64_t elem_off, const float (&v)[32], const float* __restrict__ sc,
+                                            const float* __restrict__ sh) {
+    float a[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) a[j] = fmaxf(fmaf(v[j], __ldg(sc + j), __ldg(sh + j)), 0.f);
+    if (EB == 4) {
+        float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + elem_off);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            op[j] = make_float4(round_tf32(a[4 * j]), round_tf32(a[4 * j + 1]), round_tf32(a[4 * j + 2]), round_tf32(a[4 * j + 3]));
+    } else {
+        uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(out) + elem_off);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            __half2 h0 = __floats2half2_rn(a[8 * j], a[8 * j + 1]), h1 = __floats2half2_rn(a[8 * j + 2], a[8 * j + 3]);
+            __half2 h2 = __floats2half2_rn(a[8 * j + 4], a[8 * j + 5]), h3 = __floats2half2_rn(a[8 * j + 6], a[8 * j + 7]);
+            op[j] = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                               *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+        }
+    }
+}
+template <int EB>
+__device__ __forceinline__ void store_act1(void* out, int64_t e, float a) {
+    if (EB == 4) reinterpret_cast<float*>(out)[e] = round_tf32(a);
+    else reinterpret_cast<__half*>(out)[e] = __float2half_rn(a);
+}
+
 struct Launch {   // per-launch scalars (kernel parameter)
     int num_tiles;     // row tiles
     int splits;        // CTAs sharing one tile's K range (1 = fused epilogue)
@@ -167,12 +210,12 @@ struct Launch {   // per-launch scalars (kernel parameter)
 };
 
 struct Layout {  // dynamic shared memory carve-up (1024 B aligned base)
-    uint32_t a0, b0, b_stage_bytes;
+    uint32_t a0, b0, a_stage_bytes, b_stage_bytes;
     uint32_t full0, empty0, tfull0, tempty0, tmem_slot, idx0;
     __device__ __forceinline__ uint32_t idx(uint32_t buf, int row, int col) const {
         return idx0 + buf * IDX_BUF_BYTES + (uint32_t)(row * BM + col) * 4u;
     }
-    __device__ __forceinline__ uint32_t a(uint32_t s) const { return a0 + s * A_STAGE_BYTES; }
+    __device__ __forceinline__ uint32_t a(uint32_t s) const { return a0 + s * a_stage_bytes; }
     __device__ __forceinline__ uint32_t b(uint32_t s) const { return b0 + s * b_stage_bytes; }
     __device__ __forceinline__ uint32_t full(uint32_t s) const { return full0 + 8 * s; }
     __device__ __forceinline__ uint32_t empty(uint32_t s) const { return empty0 + 8 * s; }
@@ -188,11 +231,12 @@ struct Layout {  // dynamic shared memory carve-up (1024 B aligned base)
     }
 };
 
-__device__ __forceinline__ Layout carve(uint32_t base, int n, int stages) {
+__device__ __forceinline__ Layout carve(uint32_t base, int n, int stages, int row_bytes) {
     Layout L;
     L.a0 = base;
-    L.b0 = base + stages * A_STAGE_BYTES;
-    L.b_stage_bytes = n * 128;
+    L.a_stage_bytes = BM * row_bytes;
+    L.b0 = base + stages * L.a_stage_bytes;
+    L.b_stage_bytes = n * row_bytes;
     L.idx0 = L.b0 + stages * L.b_stage_bytes;
     uint32_t off = L.idx0 + 2 * IDX_BUF_BYTES;
     L.full0 = off;
@@ -202,8 +246,8 @@ __device__ __forceinline__ Layout carve(uint32_t base, int n, int stages) {
     L.tmem_slot = L.tfull0 + 64;
     return L;
 }
-static inline size_t smem_bytes(int n, int stages) {
-    return 1024 + (size_t)stages * (A_STAGE_BYTES + (size_t)n * 128) + 2 * IDX_BUF_BYTES + 16 * MAX_STAGES + 128;
+static inline size_t smem_bytes(int n, int stages, int row_bytes) {
+    return 1024 + (size_t)stages * ((size_t)BM * row_bytes + (size_t)n * row_bytes) + 2 * IDX_BUF_BYTES + 16 * MAX_STAGES + 128;
 }
 
 __device__ __forceinline__ uint32_t seg_mask(const tl_conv_seg& sg, int64_t tile) {
@@ -227,11 +271,17 @@ __device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
 //   warp  20      MMA issuer (lane 0) + TMEM alloc/dealloc
 //   warp  21      scheduler: one work item ahead it stages the item's rulebook rows (cp.async) and the list of live
 //                 (segment, offset, k-block) chunks in shared memory, so nobody else evaluates masks or split ranges
+template <int EB>   // bytes per operand element: 4 = fp32 storage / kind::tf32, 2 = fp16 storage / kind::f16
 __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const tl_conv_desc d, const Launch P) {
+    constexpr int ROW = BK * EB;          // bytes per operand row in a stage (one swizzle row)
+    constexpr int CH = ROW / 16;          // 16 B chunks per row
+    constexpr int RPI = 32 / CH;          // rows covered by one warp-wide LDGSTS
+    constexpr int NI = 32 / RPI;          // LDGSTS per thread per A tile
+    constexpr int KSTEPS = ROW / 32;      // UMMA K steps (32 B each) per stage
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int N = d.c_out;
-    const Layout L = carve(base, N, P.stages);
+    const Layout L = carve(base, N, P.stages, ROW);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (L.tmem_slot - smem_u32(smem_raw)));
     const uint32_t S = (uint32_t)P.stages;
@@ -312,17 +362,20 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const tl_conv_desc d, c
         // chunks are in flight per CTA.
         const int group = warp >> 2, gw = warp & 3;       // producer group, warp within group
         const int ptid = threadIdx.x & 127;               // thread within group
-        const int chunk = lane & 7, sub = lane >> 3;
+        const int chunk = lane % CH, sub = lane / CH;
         const int col = gw * 32 + lane;                   // tile row whose rulebook entry this thread reads
-        uint32_t a_off[8];
+        // 16 B chunk c of row r lives at chunk c ^ (r & 7) (128 B rows, SWIZZLE_128B) or c ^ ((r >> 1) & 3) (64 B, SWIZZLE_64B)
+        auto swz = [](int c, int r) { return ROW == 128 ? (c ^ (r & 7)) : (c ^ ((r >> 1) & 3)); };
+        uint32_t a_off[NI];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int rl = i * 4 + sub;
-            a_off[i] = (uint32_t)((gw * 32 + rl) * 128 + ((chunk ^ (rl & 7)) << 4));
+        for (int i = 0; i < NI; ++i) {
+            const int rl = i * RPI + sub;
+            a_off[i] = (uint32_t)((gw * 32 + rl) * ROW + (swz(chunk, rl) << 4));
         }
-        const int brow = ptid >> 3;                       // B rows brow + 16 j
-        const uint32_t b_off0 = (uint32_t)(brow * 128 + ((chunk ^ (brow & 7)) << 4));
-        const int nb = N >> 4;
+        constexpr int BROWS = 128 / CH;                   // B rows copied per pass of the group's 128 threads
+        const int brow = ptid / CH;                       // B rows brow + BROWS j
+        const uint32_t b_off0 = (uint32_t)(brow * ROW + (swz(chunk, brow) << 4));
+        const int nb = N / BROWS;
         const uint32_t G = (uint32_t)P.groups;
         uint32_t my_next = (uint32_t)group;    // ordinal (in this CTA's chunk stream) of my group's next chunk
         uint32_t c0 = 0;                       // ordinal of the current work item's first chunk
@@ -335,9 +388,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const tl_conv_desc d, c
             mbar_wait(L.wfull(buf), (witer >> 1) & 1u);
             const uint32_t n = ld_shared_u32(L.count(buf));
             uint32_t prev_sk = 0xffffffffu;
-            const float* rp[8];
+            const char* rp[NI];
             uint32_t vmask = 0;
-            const float* wk = nullptr;
+            const char* wk = nullptr;
             int64_t wrow_stride = 0;
             while (my_next < c0 + n) {
                 const uint32_t e = ld_shared_u32(L.list(buf, (int)(my_next - c0)));
@@ -351,29 +404,29 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const tl_conv_desc d, c
                     else my_row = (row0 + col) < d.n_out ? (int)(row0 + col) : -1;
                     vmask = 0;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int r = __shfl_sync(0xffffffffu, my_row, i * 4 + sub);
+                    for (int i = 0; i < NI; ++i) {
+                        const int r = __shfl_sync(0xffffffffu, my_row, i * RPI + sub);
                         vmask |= (r >= 0 ? 1u : 0u) << i;
-                        rp[i] = sg.src + (int64_t)max(r, 0) * sg.src_stride + chunk * 4;
+                        rp[i] = reinterpret_cast<const char*>(sg.src) + (int64_t)max(r, 0) * sg.src_stride * EB + chunk * 16;
                     }
-                    wk = sg.weight + ((int64_t)k * N + brow) * sg.c_in + chunk * 4;
-                    wrow_stride = (int64_t)16 * sg.c_in;
+                    wk = reinterpret_cast<const char*>(sg.weight) + ((int64_t)k * N + brow) * sg.c_in * EB + chunk * 16;
+                    wrow_stride = (int64_t)BROWS * sg.c_in * EB;
                 }
                 mbar_wait(L.empty(slot), phase ^ 1u);
                 const uint32_t a_st = L.a(slot), b_st = L.b(slot) + b_off0;
                 if (P.debug & 2) {
                 } else if (P.use_cg) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        cp_async16_cg(a_st + a_off[i], rp[i] + kb * BK, ((vmask >> i) & 1u) ? 16u : 0u);
+                    for (int i = 0; i < NI; ++i)
+                        cp_async16_cg(a_st + a_off[i], rp[i] + kb * ROW, ((vmask >> i) & 1u) ? 16u : 0u);
                 } else {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        cp_async16(a_st + a_off[i], rp[i] + kb * BK, ((vmask >> i) & 1u) ? 16u : 0u);
+                    for (int i = 0; i < NI; ++i)
+                        cp_async16(a_st + a_off[i], rp[i] + kb * ROW, ((vmask >> i) & 1u) ? 16u : 0u);
                 }
                 if (!(P.debug & 8)) {
-                    const float* wp = wk + kb * BK;
-                    for (int j = 0; j < nb; ++j) cp_async16(b_st + j * 2048, wp + j * wrow_stride, 16u);
+                    const char* wp = wk + kb * ROW;
+                    for (int j = 0; j < nb; ++j) cp_async16(b_st + j * (BROWS * ROW), wp + j * wrow_stride, 16u);
                 }
                 cp_async_mbar_arrive_noinc(L.full(slot));
                 my_next += G;
@@ -449,22 +502,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const tl_conv_desc d, c
                             for (int j = 0; j < 8; ++j)
                                 op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                         }
-#pragma unroll
-                        for (int which = 0; which < 2; ++which) {
-                            float* outp = which ? d.out_act2 : d.out_act1;
-                            if (!outp) continue;
-                            float4* op = reinterpret_cast<float4*>(outp + o);
-                            const float4* sp = reinterpret_cast<const float4*>((which ? d.scale2 : d.scale1) + c0);
-                            const float4* tp = reinterpret_cast<const float4*>((which ? d.shift2 : d.shift1) + c0);
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const float4 s4 = __ldg(sp + j), t4 = __ldg(tp + j);
-                                op[j] = make_float4(round_tf32(fmaxf(fmaf(v[4 * j], s4.x, t4.x), 0.f)),
-                                                    round_tf32(fmaxf(fmaf(v[4 * j + 1], s4.y, t4.y), 0.f)),
-                                                    round_tf32(fmaxf(fmaf(v[4 * j + 2], s4.z, t4.z), 0.f)),
-                                                    round_tf32(fmaxf(fmaf(v[4 * j + 3], s4.w, t4.w), 0.f)));
-                            }
-                        }
+                        if (d.out_act1) store_act32<EB>(d.out_act1, o, v, d.scale1 + c0, d.shift1 + c0);
+                        if (d.out_act2) store_act32<EB>(d.out_act2, o, v, d.scale2 + c0, d.shift2 + c0);
                     }
                 }
             }
@@ -474,9 +513,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const tl_conv_desc d, c
     } else if (warp == kMmaWarp) {
         // ===================== MMA issuer (one elected thread) ======================================
         if (lane == 0) {
-            const uint32_t idesc = make_idesc_tf32(N);
-            const uint64_t adesc0 = make_smem_desc(L.a0), bdesc0 = make_smem_desc(L.b0);
-            const uint32_t a_step = A_STAGE_BYTES >> 4, b_step = L.b_stage_bytes >> 4;
+            const uint32_t idesc = make_idesc(N, EB == 2);
+            const uint64_t adesc0 = make_smem_desc(L.a0, ROW), bdesc0 = make_smem_desc(L.b0, ROW);
+            const uint32_t a_step = L.a_stage_bytes >> 4, b_step = L.b_stage_bytes >> 4;
             const uint32_t wmask = (uint32_t)(P.acc_ways - 1);
             uint32_t slot = 0, phase = 0, titer = 0;
             for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++titer) {
@@ -494,11 +533,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const tl_conv_desc d, c
                     const uint64_t bdesc = bdesc0 + (uint64_t)(slot * b_step);
                     if (!(P.debug & 1)) {
 #pragma unroll
-                        for (int kk = 0; kk < BK / 8; ++kk) {  // UMMA_K = 8 for tf32: advance 32 B inside the swizzle atom
+                        for (int kk = 0; kk < KSTEPS; ++kk) {  // UMMA K step = 32 B (8 tf32 / 16 fp16): advance inside the swizzle atom
                             // K-step kk accumulates into its own TMEM tile kk % ways (the epilogue adds the tiles up)
                             const uint32_t way = (uint32_t)kk & wmask;
-                            umma_tf32(tmem_d + way * P.acc_cols, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2),
-                                      idesc, (c == 0 && (uint32_t)kk <= wmask) ? 0u : 1u);
+                            if (EB == 4)
+                                umma_tf32(tmem_d + way * P.acc_cols, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2),
+                                          idesc, (c == 0 && (uint32_t)kk <= wmask) ? 0u : 1u);
+                            else
+                                umma_f16(tmem_d + way * P.acc_cols, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2),
+                                         idesc, (c == 0 && (uint32_t)kk <= wmask) ? 0u : 1u);
                         }
                     }
                     umma_commit(L.empty(slot));
@@ -520,6 +563,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const tl_conv_desc d, c
 }
 
 // split-K second pass: v = ws (+ residual) -> raw / act outputs
+template <int EB>
 __global__ void k_splitk_epilogue(const tl_conv_desc d, const float* __restrict__ ws) {
     const int64_t total = (int64_t)d.n_out * d.c_out;
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
@@ -527,8 +571,8 @@ __global__ void k_splitk_epilogue(const tl_conv_desc d, const float* __restrict_
         float v = ws[e];
         if (d.residual) v += __ldg(d.residual + e);
         if (d.out_raw) d.out_raw[e] = v;
-        if (d.out_act1) d.out_act1[e] = round_tf32(fmaxf(fmaf(v, __ldg(d.scale1 + col), __ldg(d.shift1 + col)), 0.f));
-        if (d.out_act2) d.out_act2[e] = round_tf32(fmaxf(fmaf(v, __ldg(d.scale2 + col), __ldg(d.shift2 + col)), 0.f));
+        if (d.out_act1) store_act1<EB>(d.out_act1, e, fmaxf(fmaf(v, __ldg(d.scale1 + col), __ldg(d.shift1 + col)), 0.f));
+        if (d.out_act2) store_act1<EB>(d.out_act2, e, fmaxf(fmaf(v, __ldg(d.scale2 + col), __ldg(d.shift2 + col)), 0.f));
     }
 }
 
@@ -536,6 +580,7 @@ __global__ void k_splitk_epilogue(const tl_conv_desc d, const float* __restrict_
 // 4-channel input convolution (tree_learn.py:37-39): K = 4 is below one UMMA K block, so it runs as SIMT:
 // one thread per voxel, 27 gathered float4 rows, weights [27][4][32] broadcast from shared memory.
 // ------------------------------------------------------------------------------------------------
+template <int EB>
 __global__ void __launch_bounds__(128) k_conv_in4(const tl_conv_desc d) {
     __shared__ __align__(16) float ws[27 * 4 * 32];
     const tl_conv_seg& sg = d.seg[0];
@@ -572,20 +617,8 @@ __global__ void __launch_bounds__(128) k_conv_in4(const tl_conv_desc d) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) op[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
     }
-#pragma unroll
-    for (int which = 0; which < 2; ++which) {
-        float* outp = which ? d.out_act2 : d.out_act1;
-        if (!outp) continue;
-        const float* sc = which ? d.scale2 : d.scale1;
-        const float* sh = which ? d.shift2 : d.shift1;
-        float4* op = reinterpret_cast<float4*>(outp + o);
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-            op[j] = make_float4(round_tf32(fmaxf(fmaf(acc[4 * j], sc[4 * j], sh[4 * j]), 0.f)),
-                                round_tf32(fmaxf(fmaf(acc[4 * j + 1], sc[4 * j + 1], sh[4 * j + 1]), 0.f)),
-                                round_tf32(fmaxf(fmaf(acc[4 * j + 2], sc[4 * j + 2], sh[4 * j + 2]), 0.f)),
-                                round_tf32(fmaxf(fmaf(acc[4 * j + 3], sc[4 * j + 3], sh[4 * j + 3]), 0.f)));
-    }
+    if (d.out_act1) store_act32<EB>(d.out_act1, o, acc, d.scale1, d.shift1);
+    if (d.out_act2) store_act32<EB>(d.out_act2, o, acc, d.scale2, d.shift2);
 }
 
 }  // namespace tc
@@ -610,23 +643,31 @@ static int conv_fwd_simt_fallback_note(const tl_conv_desc&, cudaStream_t) {
     return TL_ERR_UNSUPPORTED;
 }
 
-int conv_fwd_tc(const tl_conv_desc& d, cudaStream_t stream) {
+int conv_fwd_tc(const tl_conv_desc& d, cudaStream_t stream, bool half) {
     if (d.n_seg == 1 && d.seg[0].c_in == 4 && d.c_out == 32 && d.seg[0].index && d.seg[0].src_stride == 4) {
-        tc::k_conv_in4<<<(unsigned)((d.n_out + 127) / 128), 128, 0, stream>>>(d);
+        // the 4-channel network input is always fp32; only the activated output follows the operand format
+        if (half) tc::k_conv_in4<2><<<(unsigned)((d.n_out + 127) / 128), 128, 0, stream>>>(d);
+        else tc::k_conv_in4<4><<<(unsigned)((d.n_out + 127) / 128), 128, 0, stream>>>(d);
         TL_LAUNCH_CHECK();
         return TL_OK;
     }
-    if (!tc_eligible(d)) return conv_fwd_simt(d, stream);
+    if (!tc_eligible(d)) {
+        if (half) {
+            set_error("tl_conv_fwd(f16): shape not eligible for the tcgen05 path (c_in %% 32, c_out %% 32, c_out <= 256)");
+            return TL_ERR_UNSUPPORTED;
+        }
+        return conv_fwd_simt(d, stream);
+    }
+    const int row_bytes = half ? 64 : 128;
     static int num_sms = 0, smem_budget = 0, split_target = 0;
     if (!num_sms) {
         int dev = 0;
         TL_CUDA_CHECK(cudaGetDevice(&dev));
         TL_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-        TL_CUDA_CHECK(cudaFuncSetAttribute(tc::k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        TL_CUDA_CHECK(cudaFuncSetAttribute(tc::k_conv_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        TL_CUDA_CHECK(cudaFuncSetAttribute(tc::k_conv_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         smem_budget = env_int("TL_TC_SMEM_KB", 200) * 1024;   // keep the rest of the 228 KB as L1 for the gather
         split_target = env_int("TL_TC_SPLIT_WAVES", 2);        // split-K until work items >= waves * SMs
-        TL_CUDA_CHECK(cudaFuncSetAttribute(tc::k_conv_tc, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                           env_int("TL_TC_CARVEOUT", 58)));
     }
     const int n = d.c_out;
     tc::Launch P;
@@ -634,14 +675,14 @@ int conv_fwd_tc(const tl_conv_desc& d, cudaStream_t stream) {
     while (P.acc_cols < n) P.acc_cols <<= 1;
     P.debug = env_int("TL_TC_DEBUG", 0);
     P.acc_ways = env_int("TL_TC_WAYS", 4);
-    while (P.acc_ways > 1 && 2 * P.acc_ways * P.acc_cols > 512) P.acc_ways >>= 1;
+    while (P.acc_ways > 1 && (2 * P.acc_ways * P.acc_cols > 512 || P.acc_ways > row_bytes / 32)) P.acc_ways >>= 1;
     P.buf_cols = P.acc_ways * P.acc_cols;
     P.tmem_cols = 2 * P.buf_cols;  // <= 512
-    const size_t stage = tc::A_STAGE_BYTES + (size_t)n * 128;
+    const size_t stage = (size_t)(tc::BM + n) * row_bytes;
     int stages = (int)((smem_budget - 2048 - 2 * tc::IDX_BUF_BYTES) / stage);
     if (stages < 4) stages = 4;
     if (stages > tc::MAX_STAGES) stages = tc::MAX_STAGES;
-    while (tc::smem_bytes(n, stages) > 227 * 1024 && stages > 2) --stages;
+    while (tc::smem_bytes(n, stages, row_bytes) > 227 * 1024 && stages > 2) --stages;
     P.stages = stages;
     // two producer groups alternate chunks, each keeps `lag` of its own cp.async groups in flight before publishing
     // the oldest; 2*lag < stages keeps the ring deadlock-free (a group can always publish what the MMA waits for)
@@ -651,7 +692,7 @@ int conv_fwd_tc(const tl_conv_desc& d, cudaStream_t stream) {
     P.lag = (stages - 1) / groups;     // G * lag < stages: the ring cannot deadlock
     if (P.lag < 1) P.lag = 1;
     P.use_cg = env_int("TL_TC_CG", 1);
-    const size_t smem = tc::smem_bytes(n, stages);
+    const size_t smem = tc::smem_bytes(n, stages, row_bytes);
     P.num_tiles = (d.n_out + tc::BM - 1) / tc::BM;
     P.chunks_total = 0;
     for (int s = 0; s < d.n_seg; ++s) P.chunks_total += d.seg[s].n_off * (d.seg[s].c_in / tc::BK);
@@ -683,12 +724,14 @@ int conv_fwd_tc(const tl_conv_desc& d, cudaStream_t stream) {
     }
     int grid = P.num_tiles * P.splits;
     if (grid > num_sms) grid = num_sms;   // 1 CTA per SM (launch bounds); persistent over work items
-    tc::k_conv_tc<<<grid, tc::kThreads, smem, stream>>>(d, P);
+    if (half) tc::k_conv_tc<2><<<grid, tc::kThreads, smem, stream>>>(d, P);
+    else tc::k_conv_tc<4><<<grid, tc::kThreads, smem, stream>>>(d, P);
     TL_LAUNCH_CHECK();
     if (P.splits > 1) {
         const int64_t total = (int64_t)d.n_out * d.c_out;
-        tc::k_splitk_epilogue<<<(unsigned)((total + 255) / 256 > 1184 ? 1184 : (total + 255) / 256), 256, 0, stream>>>(
-            d, d.splitk_ws);
+        const unsigned eg = (unsigned)((total + 255) / 256 > 1184 ? 1184 : (total + 255) / 256);
+        if (half) tc::k_splitk_epilogue<2><<<eg, 256, 0, stream>>>(d, d.splitk_ws);
+        else tc::k_splitk_epilogue<4><<<eg, 256, 0, stream>>>(d, d.splitk_ws);
         TL_LAUNCH_CHECK();
     }
     return TL_OK;

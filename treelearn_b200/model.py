@@ -77,7 +77,9 @@ class TreeLearn(nn.Module):
         self.use_feats, self.use_coords = use_feats, use_coords
         self.spatial_shape = spatial_shape
         self.max_num_points_per_voxel = max_num_points_per_voxel
-        self.mode = mode                      # 'fp32' (SIMT, exact-ish) or 'tf32' (tcgen05)
+        self.mode = mode                      # 'fp32' (SIMT, exact-ish), 'tf32' or 'f16' (tcgen05; f16 = fp16 operands)
+        if mode == 'f16' and channels % 32 != 0:
+            raise ValueError("mode='f16' needs channels % 32 == 0 (every conv must take the tcgen05 path)")
         self.planes = [channels * (i + 1) for i in range(num_blocks)]
         self._norm = functools.partial(nn.BatchNorm1d, eps=BN_EPS, momentum=BN_MOMENTUM)
         self._packed = None
@@ -150,7 +152,8 @@ class TreeLearn(nn.Module):
         key = self._version_key()
         if self._packed is not None and self._packed['key'] == key:
             return self._packed
-        tf32 = self.mode == 'tf32'
+        tf32 = self.mode in ('tf32', 'f16')
+        half = self.mode == 'f16'
         pk = {'key': key}
         with torch.no_grad():
             for name, m in self.named_modules():
@@ -165,7 +168,9 @@ class TreeLearn(nn.Module):
                         pieces = [w]
                     out = []
                     for piece in pieces:
-                        if tf32 and tc_eligible(piece.shape[2], co):
+                        if half and tc_eligible(piece.shape[2], co) and 'i_branch' not in name:
+                            out.append(piece.permute(1, 0, 2).contiguous().half())          # fp16 [K, Co, Ci]
+                        elif tf32 and tc_eligible(piece.shape[2], co):
                             out.append(_round_tf32(piece.permute(1, 0, 2).contiguous()))   # [K, Co, Ci] K-major B operand
                         else:
                             out.append(piece.permute(1, 2, 0).contiguous())               # [K, Ci, Co] SIMT layout
@@ -211,7 +216,7 @@ class TreeLearn(nn.Module):
 
     def _run_backbone(self, vfeats, levels):
         pk = self._pack()
-        mode = _lib.MODE_TF32 if self.mode == 'tf32' else _lib.MODE_FP32
+        mode = {'fp32': _lib.MODE_FP32, 'tf32': _lib.MODE_TF32, 'f16': _lib.MODE_F16}[self.mode]
         g0 = levels[0]
         x, xa = sparse.conv([Seg(vfeats, pk['input_conv.0'][0], g0.nbr, g0.nbr_mask)], g0.n, self.planes[0], mode,
                             raw=True, act1=pk['unet.blocks.block0.conv_branch.0'])
@@ -239,8 +244,14 @@ class TreeLearn(nn.Module):
         e, ea = conv([Seg(ua, pk[p + '.deconv.2'][0], g.up_index, g.up_mask)], raw=True, act1=(s_cat[c:], t_cat[c:]))
         wa, wi = pk[t0 + '.conv_branch.2'], pk[t0 + '.i_branch.0']
         ha = conv([nbr(za_tail, wa[0]), nbr(ea, wa[1])], act1=pk[t0 + '.conv_branch.3'])
-        t, ta = conv([nbr(ha, pk[t0 + '.conv_branch.5'][0]), Seg(z, wi[0]), Seg(e, wi[1])], raw=True,
-                     act1=pk[t1 + '.0'])
+        if mode == _lib.MODE_F16:
+            # the 1x1 projection reads the fp32 residual-stream tensors: run it as its own TF32 launch and feed it in
+            # as the residual of the fp16-operand 3^3 conv
+            proj = sparse.conv([Seg(z, wi[0]), Seg(e, wi[1])], n, c, _lib.MODE_TF32, raw=True)
+            t, ta = conv([nbr(ha, pk[t0 + '.conv_branch.5'][0])], residual=proj, raw=True, act1=pk[t1 + '.0'])
+        else:
+            t, ta = conv([nbr(ha, pk[t0 + '.conv_branch.5'][0]), Seg(z, wi[0]), Seg(e, wi[1])], raw=True,
+                         act1=pk[t1 + '.0'])
         ha = conv([nbr(ta, pk[t1 + '.2'][0])], act1=pk[t1 + '.3'])
         return conv([nbr(ha, pk[t1 + '.5'][0])], residual=t, act1=ret_act)
 

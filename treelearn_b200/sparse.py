@@ -150,27 +150,28 @@ def conv(segs, n_out, c_out, mode, residual=None, raw=False, act1=None, act2=Non
             g.index, g.index_stride, g.tile_mask = ptr(s.index), s.index.stride(0), ptr(s.mask)
     outs = []
     d.residual = ptr(residual)
+    act_dtype = torch.float16 if mode == _lib.MODE_F16 else torch.float32   # operand format of the consumers
     if raw:
         o = torch.empty((n_out, c_out), dtype=torch.float32, device=dev)
         d.out_raw = ptr(o)
         outs.append(o)
     if act1 is not None:
-        o = torch.empty((n_out, c_out), dtype=torch.float32, device=dev)
+        o = torch.empty((n_out, c_out), dtype=act_dtype, device=dev)
         d.out_act1, d.scale1, d.shift1 = ptr(o), ptr(act1[0]), ptr(act1[1])
         outs.append(o)
     if act2 is not None:
-        o = torch.empty((n_out, c_out), dtype=torch.float32, device=dev)
+        o = torch.empty((n_out, c_out), dtype=act_dtype, device=dev)
         d.out_act2, d.scale2, d.shift2 = ptr(o), ptr(act2[0]), ptr(act2[1])
         outs.append(o)
-    if mode == _lib.MODE_TF32 and 0 < n_out < SPLITK_MAX_ROWS:
+    if mode != _lib.MODE_FP32 and 0 < n_out < SPLITK_MAX_ROWS:
         ws = torch.empty((n_out, c_out), dtype=torch.float32, device=dev)   # deep levels: few tiles -> split-K scratch
         d.splitk_ws = ptr(ws)
     if PROFILE is not None and n_out > 0:
         # algorithmic traffic: every input row once + one output + index tables + weights
-        byts = n_out * c_out * 4
+        byts = n_out * c_out * (2 if (mode == _lib.MODE_F16 and not raw) else 4)
         flops = 0
         for s in segs:
-            byts += s.src.shape[0] * s.src.shape[1] * 4 + s.weight.numel() * 4
+            byts += s.src.shape[0] * s.src.shape[1] * s.src.element_size() + s.weight.numel() * s.weight.element_size()
             if s.index is not None:
                 byts += s.weight.shape[0] * n_out * 4
             flops += 2 * s.weight.shape[0] * n_out * s.src.shape[1] * c_out    # dense upper bound (all offsets present)
@@ -193,7 +194,7 @@ def heads(voxel_feats, v2p, packed):
     feats = torch.empty((n, c), dtype=torch.float32, device=dev)
     logits = torch.empty((n, 2), dtype=torch.float32, device=dev)
     offs = torch.empty((n, 3), dtype=torch.float32, device=dev)
-    check(lib.tl_heads_fwd(ptr(voxel_feats), ptr(v2p), n, c, ptr(packed['sem_w1']), ptr(packed['sem_b1']),
+    check(lib.tl_heads_fwd(ptr(voxel_feats), int(voxel_feats.dtype == torch.float16), ptr(v2p), n, c, ptr(packed['sem_w1']), ptr(packed['sem_b1']),
                            ptr(packed['sem_w2']), ptr(packed['sem_b2']), ptr(packed['off_w1']), ptr(packed['off_b1']),
                            ptr(packed['off_w2']), ptr(packed['off_b2']), ptr(feats), ptr(logits), ptr(offs),
                            stream_ptr()))
