@@ -280,7 +280,7 @@ if __name__ == '__main__':
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='cfg2_2M')
-    ap.add_argument('--mode', default='tf32', choices=['fp32', 'tf32', 'f16'])
+    ap.add_argument('--mode', default='f16', choices=['fp32', 'tf32', 'f16'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     a = ap.parse_args()
     if a.impl == 'reference':

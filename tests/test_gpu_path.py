@@ -395,3 +395,13 @@ def test_f16_matches_fp32_path_on_larger_tile():
     err = (outs['f16']['offset_predictions'] - outs['fp32']['offset_predictions']).abs().max().item()
     print('f16 vs fp32 offsets', err)
     assert err < 1e-3
+
+
+def test_cluster_dense_blobs_vs_oracle():
+    """Trained-model regime: every point of a tree lands on its base => thousands of points inside a few eps cells."""
+    rng = np.random.default_rng(11)
+    blobs = [rng.normal(size=(3000, 2)) * 0.08 + c for c in ([0, 0], [0.9, 0.1], [5, 5])]
+    bridge = np.stack([np.linspace(0.25, 0.65, 4), np.full(4, 0.03)], 1)      # a thin chain joining the first two blobs
+    pts = np.concatenate(blobs + [bridge, rng.uniform(-3, 8, size=(500, 2))]).astype(np.float32)
+    pts = pts[rng.permutation(len(pts))]
+    assert np.array_equal(pipeline.group_dbscan(pts, 0.15, 50, -1, 1), cluster_ref.group_dbscan_ref(pts, 0.15, 50, -1, 1))

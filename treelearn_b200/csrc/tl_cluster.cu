@@ -195,6 +195,16 @@ __global__ void k_iota(int* p, int64_t n) {
     if (i < n) p[i] = (int)i;
 }
 
+// Grid DBSCAN for min_samples = 2.  Cells have side < eps / sqrt(2): all points of a cell are mutually within eps, so a
+// cell is chained together without distance tests (k_cc_chain); two different cells need ONE witness pair within eps
+// to merge, and cells already in the same component are skipped by comparing roots (k_cc_link).  Dense blobs (every
+// point of a tree shifted onto its base) therefore cost O(points x 12 neighbour cells) instead of O(points^2).
+__global__ void k_cc_chain(const uint64_t* __restrict__ skeys, const int* __restrict__ sidx, int64_t n, int* parent) {
+    int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j >= n || j == 0) return;
+    if (skeys[j] == skeys[j - 1]) uf_union(parent, sidx[j], sidx[j - 1]);
+}
+
 __global__ void k_cc_link(const uint64_t* __restrict__ skeys, const int* __restrict__ sidx,
                           const float* __restrict__ spts, const int* __restrict__ seg_start,
                           const uint64_t* __restrict__ tkeys, const int* __restrict__ tvals, uint64_t mask, int64_t n,
@@ -206,17 +216,20 @@ __global__ void k_cc_link(const uint64_t* __restrict__ skeys, const int* __restr
     const uint64_t key = skeys[j];
     const int64_t cx = (int64_t)(key >> (2 * kAxisBits)) - kAxisBias;
     const int64_t cy = (int64_t)((key >> kAxisBits) & ((1u << kAxisBits) - 1)) - kAxisBias;
-    for (int dx = -1; dx <= 1; ++dx)
-        for (int dy = -1; dy <= 1; ++dy) {
+    // eps / cell < 2 => partners live at most 2 cells away; each unordered cell pair is visited from its "lower" cell
+    for (int dx = 0; dx <= 2; ++dx)
+        for (int dy = (dx == 0 ? 1 : -2); dy <= 2; ++dy) {
             const int seg = hash_find(tkeys, tvals, mask, cell_key3(cx + dx, cy + dy, 0));
             if (seg < 0) continue;
             const int s = seg_start[seg], e = seg_start[seg + 1];
+            if (uf_find(parent, sidx[s]) == uf_find(parent, i)) continue;   // cells already connected
             for (int j2 = s; j2 < e; ++j2) {
-                const int i2 = sidx[j2];
-                if (i2 >= i) continue;  // each unordered pair once
                 const double ddx = x - (double)spts[j2 * 2], ddy = y - (double)spts[j2 * 2 + 1];
                 const double d2 = __dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy));
-                if (d2 <= r2) uf_union(parent, i, i2);
+                if (d2 <= r2) {
+                    uf_union(parent, i, sidx[j2]);
+                    break;   // one witness pair connects the two cells
+                }
             }
         }
 }
@@ -406,14 +419,16 @@ int tl_cluster_radius_cc(const float* points_xy, int64_t n, double radius, int64
     int* valid = c.take<int>(n + 1);
     int* rank = c.take<int>(n + 1);
     TL_REQUIRE(ok && c.ok(), "tl_cluster_radius_cc: workspace too small");
-    // cells a hair wider than the radius: two points within the radius are always in adjacent cells
-    int rc = build_grid<2>(points_xy, n, radius * (1.0 + 1e-7), g, stream);
+    // cell side a hair below eps / sqrt(2): the cell diagonal stays below eps whatever the rounding of floor(x / cell)
+    int rc = build_grid<2>(points_xy, n, radius * 0.70710678118654752440 * (1.0 - 1e-7), g, stream);
     if (rc != TL_OK) return rc;
     const int T = 256;
     const unsigned nb = (unsigned)((n + T - 1) / T);
     k_iota<<<nb, T, 0, stream>>>(parent, n);
     TL_LAUNCH_CHECK();
     TL_CUDA_CHECK(cudaMemsetAsync(size, 0, sizeof(int) * n, stream));
+    k_cc_chain<<<nb, T, 0, stream>>>(g.keys_out, g.idx_out, n, parent);
+    TL_LAUNCH_CHECK();
     k_cc_link<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(g.keys_out, g.idx_out, g.spts, g.seg_start, g.tkeys,
                                                                g.tvals, g.cap - 1, n, radius * radius, parent);
     TL_LAUNCH_CHECK();

@@ -465,7 +465,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const tl_conv_desc d, c
                         if (live) {
                             float* wp = P.splitk_ws + row * N + c0;
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) atomicAdd(wp + j, __uint_as_float(acc[j]));
+                            for (int j = 0; j < 8; ++j)   // 16 B vector reductions: 4x fewer L2 atomic operations
+                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(wp + 4 * j),
+                                             "f"(__uint_as_float(acc[4 * j])), "f"(__uint_as_float(acc[4 * j + 1])),
+                                             "f"(__uint_as_float(acc[4 * j + 2])), "f"(__uint_as_float(acc[4 * j + 3]))
+                                             : "memory");
                         }
                     }
                 }
@@ -667,7 +671,7 @@ int conv_fwd_tc(const tl_conv_desc& d, cudaStream_t stream, bool half) {
         TL_CUDA_CHECK(cudaFuncSetAttribute(tc::k_conv_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         TL_CUDA_CHECK(cudaFuncSetAttribute(tc::k_conv_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         smem_budget = env_int("TL_TC_SMEM_KB", 200) * 1024;   // keep the rest of the 228 KB as L1 for the gather
-        split_target = env_int("TL_TC_SPLIT_WAVES", 2);        // split-K until work items >= waves * SMs
+        split_target = env_int("TL_TC_SPLIT_WAVES", 1);        // split-K until work items >= waves * SMs
     }
     const int n = d.c_out;
     tc::Launch P;
