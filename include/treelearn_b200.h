@@ -140,6 +140,32 @@ int tl_knn_vote(const float* ref_xyz, const int64_t* ref_labels, int64_t n_ref, 
                 int64_t n_query, int32_t k, int64_t* out_labels, void* workspace, size_t workspace_bytes,
                 void* stream);
 
+/* ---- training (SURVEY §8 a12 train mode, a16): BatchNorm1d(eps, momentum) with batch statistics applied to the
+ *      feature rows of a sparse tensor + ReLU (tree_learn/model/tree_learn.py:34, blocks.py:57-70) and its backward,
+ *      and the sparse-conv weight gradient (autograd through spconv in tools/training/train.py:40).
+ *      The data gradient of a sparse conv is tl_conv_fwd with transposed weights on the transposed rulebook
+ *      (3^3 submanifold table: same table, offsets mirrored k -> 26-k; strided maps: down_index <-> up_index).
+ * tl_bn_stats:    acc[0..c) = sum_r x[r,j], acc[c..2c) = sum_r x[r,j]^2        (fp64, zeroed by the call)
+ * tl_bn_finalize: mean, invstd = 1/sqrt(biased var + eps), scale = gamma*invstd, shift = beta - mean*scale;
+ *                 running_mean/var (nullable) get the momentum update (unbiased variance), like torch.
+ * tl_bn_relu_apply: out = relu(scale*x + shift)
+ * tl_bn_relu_bwd: dy = d_act * [scale*x+shift > 0]; dbeta = sum dy; dgamma = sum dy*xhat;
+ *                 batch_stats=1: dx = scale*(dy - dbeta/n - xhat*dgamma/n); batch_stats=0 (eval/frozen): dx = scale*dy.
+ *                 acc: [2c] fp64 scratch. */
+int tl_bn_stats(const float* x, int64_t n, int32_t c, double* acc, void* stream);
+int tl_bn_finalize(const double* acc, int64_t n, int32_t c, const float* gamma, const float* beta, float eps,
+                   float momentum, float* running_mean, float* running_var, float* mean, float* invstd, float* scale,
+                   float* shift, void* stream);
+int tl_bn_relu_apply(const float* x, int64_t n, int32_t c, const float* scale, const float* shift, float* out,
+                     void* stream);
+int tl_bn_relu_bwd(const float* x, const float* d_act, int64_t n, int32_t c, const float* scale, const float* shift,
+                   const float* mean, const float* invstd, int32_t batch_stats, double* acc, float* dx, float* dgamma,
+                   float* dbeta, void* stream);
+/* dw[k][ci][co] = sum_r src[index[k][r], ci] * d_out[r, co]   (index NULL => identity, n_off == 1); dw is overwritten */
+int tl_conv_wgrad(const float* src, int64_t src_stride, int32_t c_in, int32_t n_off, const int32_t* index,
+                  int64_t index_stride, const uint32_t* tile_mask, const float* d_out, int64_t n_out, int32_t c_out,
+                  float* dw, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,195 @@
+"""GPU parity tests of the training path (SURVEY §8 a12 train mode, a16) through the C ABI:
+sparse-conv data/weight gradients, BatchNorm(batch statistics)+ReLU forward/backward and the running-stat update,
+and a whole training step against (1) the golden produced by the reference's own model code under torch autograd
+(tests/golden/make_golden.py) and (2) the oracle's functional restatement run with autograd on the CPU."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import model_ref
+from oracle import spconv_ref as sp
+from treelearn_b200 import TreeLearn, _lib, sparse, synth
+from treelearn_b200 import autograd as ag
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+GRAD_TOL = dict(atol=3e-4, rtol=2e-3)     # fp32 path: summation order only (atomics, fp64 BN sums)
+
+
+def _levels(edge=4.0, seed=10, n_levels=2):
+    batch = synth.make_batch([synth.synth_forest(edge=edge, n_trees=2, seed=seed, ground_density=150.0)])
+    dev = 'cuda'
+    vf, vc, keys, v2p = sparse.voxelize(batch['coords'].to(dev), batch['input_feats'].to(dev), batch['batch_ids'].to(dev),
+                                        1, 0.1, False, True, 3)
+    return sparse.build_levels(keys, vc, [500, 500, 1000], n_levels), vc
+
+
+@pytest.mark.parametrize('ci,co,mode', [(8, 16, 'fp32'), (32, 32, 'fp32'), (32, 64, 'tf32'), (64, 32, 'tf32')])
+def test_subm_conv_grads_vs_oracle_autograd(ci, co, mode):
+    (lv, _), vc = _levels()
+    nbr = sp.subm_neighbour_table(vc.cpu().numpy(), [500, 500, 1000], 3)
+    g = torch.Generator().manual_seed(ci + co)
+    x = torch.randn((lv.n, ci), generator=g)
+    w = torch.randn((co, 3, 3, 3, ci), generator=g) / (27 * ci) ** 0.5
+    gy = torch.randn((lv.n, co), generator=g)
+    xr, wr = x.clone().requires_grad_(), w.clone().requires_grad_()
+    model_ref._subm(xr, nbr, wr).backward(gy)
+    xc, wc = x.cuda().requires_grad_(), w.cuda().requires_grad_()
+    m = _lib.MODE_FP32 if mode == 'fp32' else _lib.MODE_TF32
+    ag.sparse_conv(xc, wc, ag.subm_geom(lv), m).backward(gy.cuda())
+    tol = GRAD_TOL if mode == 'fp32' else dict(atol=2e-2, rtol=2e-2)   # TF32 operands (10-bit mantissa) in fwd/dgrad
+    assert torch.allclose(xc.grad.cpu(), xr.grad, **tol)
+    # wgrad always accumulates in fp32 SIMT: tight in both modes relative to its scale (sum over ~1e4 rows)
+    scale = wr.grad.abs().max().item()
+    assert (wc.grad.cpu() - wr.grad).abs().max().item() < 2e-4 * max(scale, 1.0)
+
+
+def test_strided_inverse_and_1x1_grads_vs_oracle_autograd():
+    (lv, nx), vc = _levels()
+    out_idx, out_shape, in_row, kappa, out_row = sp.strided_pairs(vc.cpu().numpy(), [500, 500, 1000])
+    where = {tuple(r): i for i, r in enumerate(nx.coords.cpu().numpy().tolist())}
+    out_row = np.array([where[tuple(r)] for r in out_idx.tolist()])[out_row]
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn((lv.n, 8), generator=g)
+    wd = torch.randn((16, 2, 2, 2, 8), generator=g) / 8
+    wu = torch.randn((8, 2, 2, 2, 16), generator=g) / 8
+    w1 = torch.randn((12, 1, 1, 1, 8), generator=g) / 3
+    gy = torch.randn((lv.n, 12), generator=g)
+    ref = [t.clone().requires_grad_() for t in (x, wd, wu, w1)]
+    d = model_ref._pairs_conv(ref[0], ref[1], in_row, kappa, out_row, len(out_idx))
+    u = model_ref._pairs_conv(d, ref[2], out_row, kappa, in_row, lv.n)
+    (u @ ref[3].reshape(12, 8).T).backward(gy)
+    mine = [t.cuda().requires_grad_() for t in (x, wd, wu, w1)]
+    d = ag.sparse_conv(mine[0], mine[1], ag.down_geom(lv, nx), _lib.MODE_FP32)
+    u = ag.sparse_conv(d, mine[2], ag.up_geom(lv, nx), _lib.MODE_FP32)
+    ag.sparse_conv(u, mine[3], ag.identity_geom(lv.n), _lib.MODE_FP32).backward(gy.cuda())
+    for a, b, name in zip(mine, ref, ('x', 'w_down', 'w_up', 'w_1x1')):
+        assert torch.allclose(a.grad.cpu(), b.grad, **GRAD_TOL), name
+
+
+@pytest.mark.parametrize('n,c,training', [(5000, 32, True), (777, 24, True), (3000, 96, False), (100000, 224, True)])
+def test_bn_relu_forward_backward_and_running_stats_vs_torch(n, c, training):
+    g = torch.Generator().manual_seed(n + c)
+    x = torch.randn((n, c), generator=g) * 2 + 0.5
+    gy = torch.randn((n, c), generator=g)
+    bn_ref = torch.nn.BatchNorm1d(c, eps=1e-4, momentum=0.1)
+    with torch.no_grad():
+        bn_ref.weight.copy_(torch.rand(c, generator=g) + 0.5)
+        bn_ref.bias.copy_(torch.randn(c, generator=g) * 0.2)
+        bn_ref.running_mean.copy_(torch.randn(c, generator=g) * 0.1)
+        bn_ref.running_var.copy_(torch.rand(c, generator=g) + 0.5)
+    bn = torch.nn.BatchNorm1d(c, eps=1e-4, momentum=0.1)
+    bn.load_state_dict(bn_ref.state_dict())
+    bn = bn.cuda()
+    bn_ref.train(training)
+    bn.train(training)
+    xr = x.clone().requires_grad_()
+    ref_out = F.relu(bn_ref(xr))
+    ref_out.backward(gy)
+    xc = x.cuda().requires_grad_()
+    out = ag.bn_relu(xc, bn)
+    out.backward(gy.cuda())
+    assert torch.allclose(out.detach().cpu(), ref_out.detach(), atol=2e-5, rtol=1e-5)
+    assert torch.allclose(xc.grad.cpu(), xr.grad, atol=2e-5, rtol=1e-4)
+    assert torch.allclose(bn.weight.grad.cpu(), bn_ref.weight.grad, atol=2e-3, rtol=1e-4)
+    assert torch.allclose(bn.bias.grad.cpu(), bn_ref.bias.grad, atol=2e-3, rtol=1e-4)
+    assert torch.allclose(bn.running_mean.cpu(), bn_ref.running_mean, atol=1e-6, rtol=1e-5)
+    assert torch.allclose(bn.running_var.cpu(), bn_ref.running_var, atol=1e-6, rtol=1e-5)
+    assert int(bn.num_batches_tracked) == int(bn_ref.num_batches_tracked)
+
+
+def _fixture():
+    g = np.load(os.path.join(GOLD, 'model_small.npz'))
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith('sd:')}
+    batch = {k[6:]: torch.from_numpy(g[k]) for k in g.files if k.startswith('batch:')}
+    batch['batch_size'] = int(batch['batch_size'])
+    return g, sd, batch
+
+
+def test_training_step_matches_reference_code_golden():
+    """Loss and gradients of one training-mode step (BN batch statistics, autograd) recorded from the reference's own
+    tree_learn/model/{tree_learn,blocks}.py (tests/golden/make_golden.py)."""
+    g, sd, batch = _fixture()
+    net = TreeLearn(channels=8, num_blocks=3, use_feats=True, use_coords=False, spatial_shape=[500, 500, 1000])
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda().train()
+    loss, ld = net(batch, return_loss=True)
+    loss.backward()
+    assert abs(loss.item() - float(g['train_loss'])) < 1e-3
+    grads = dict(net.named_parameters())
+    for key in [k for k in g.files if k.startswith('grad:')]:
+        ref = torch.from_numpy(g[key])
+        mine = grads[key[5:]].grad.cpu()
+        scale = max(ref.abs().max().item(), 1e-2)
+        assert (mine - ref).abs().max().item() < 2e-3 * scale, (key, (mine - ref).abs().max().item(), scale)
+    # every parameter received a gradient (nothing was silently detached)
+    assert all(p.grad is not None for p in net.parameters())
+
+
+def test_training_step_running_stats_and_all_grads_vs_oracle():
+    """All parameter gradients + updated BN running statistics vs the oracle's functional restatement under CPU autograd."""
+    g, sd, batch = _fixture()
+    sd_ref = {k: (v.clone().requires_grad_() if v.is_floating_point() and 'running' not in k else v.clone())
+              for k, v in sd.items()}
+    new_stats = {}
+    out = model_ref.forward_ref(sd_ref, batch, use_coords=False, use_feats=True, spatial_shape=[500, 500, 1000],
+                                training=True, new_stats=new_stats)
+    loss_ref, _ = model_ref.loss_ref(out, batch)
+    loss_ref.backward()
+    net = TreeLearn(channels=8, num_blocks=3, use_feats=True, use_coords=False, spatial_shape=[500, 500, 1000])
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda().train()
+    loss, _ = net(batch, return_loss=True)
+    loss.backward()
+    assert abs(loss.item() - loss_ref.item()) < 1e-3
+    for name, p in net.named_parameters():
+        ref = sd_ref[name].grad
+        scale = max(ref.abs().max().item(), 1e-2)
+        assert (p.grad.cpu() - ref).abs().max().item() < 2e-3 * scale, name
+    mine = net.state_dict()
+    for k, v in new_stats.items():
+        assert torch.allclose(mine[k].cpu(), v, atol=1e-5, rtol=1e-4), k
+
+
+def test_training_step_tf32_default_width_close_to_fp32():
+    """Default channel width (32): tcgen05 TF32 forward/dgrad + fp32 wgrad stay close to the all-fp32 path."""
+    batch = synth.make_batch([synth.synth_forest(edge=5.0, n_trees=3, seed=3, ground_density=150.0)], inner_edge=3.0)
+    sd = model_ref.make_state_dict(channels=32, num_blocks=4, seed=2)
+    res = {}
+    for mode in ('fp32', 'tf32'):
+        net = TreeLearn(channels=32, num_blocks=4, use_feats=False, use_coords=False, spatial_shape=[500, 500, 1000],
+                        mode=mode)
+        net.load_state_dict(sd)
+        net = net.cuda().train()
+        loss, _ = net(batch, return_loss=True)
+        loss.backward()
+        res[mode] = (loss.item(), {n: p.grad.clone() for n, p in net.named_parameters()})
+    assert abs(res['fp32'][0] - res['tf32'][0]) < 2e-2 * max(abs(res['fp32'][0]), 1.0)
+    for n, gref in res['fp32'][1].items():
+        cos = F.cosine_similarity(gref.flatten(), res['tf32'][1][n].flatten(), dim=0).item()
+        assert cos > 0.98 or gref.abs().max().item() < 1e-6, (n, cos)
+
+
+def test_frozen_modules_and_optimizer_step():
+    """fixed_modules freeze parameters and keep their BatchNorm in eval (reference tree_learn.py:47-72); an AdamW step
+    on the rest changes the loss (tools/training/train.py:35-44)."""
+    g, sd, batch = _fixture()
+    net = TreeLearn(channels=8, num_blocks=3, use_feats=True, use_coords=False, spatial_shape=[500, 500, 1000],
+                    fixed_modules=['input_conv', 'unet'])
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda().train()
+    before = {k: v.clone() for k, v in net.state_dict().items()}
+    opt = torch.optim.AdamW([p for p in net.parameters() if p.requires_grad], lr=1e-2)
+    loss0, _ = net(batch, return_loss=True)
+    loss0.backward()
+    assert all(p.grad is None for n, p in net.named_parameters() if n.startswith(('input_conv', 'unet')))
+    opt.step()
+    after = net.state_dict()
+    for k in before:
+        if k.startswith(('input_conv', 'unet')):
+            assert torch.equal(before[k], after[k]), k        # frozen weights AND frozen BN running stats
+    loss1, _ = net(batch, return_loss=True)
+    assert loss1.item() != loss0.item()

@@ -1,0 +1,308 @@
+// Training-only kernels (SURVEY §8 a12 train mode, a16): BatchNorm batch statistics, BN+ReLU forward and
+// backward, and the sparse-conv weight gradient.  The data gradient of every sparse conv reuses tl_conv_fwd
+// (same rulebook, transposed weights; offsets mirrored for the 3^3 submanifold table) -- see autograd.py.
+//
+// Reference semantics: torch.nn.BatchNorm1d(eps=1e-4, momentum=0.1) applied to SparseConvTensor.features
+// (tree_learn/model/tree_learn.py:34, blocks.py:57-70): normalise with the biased batch variance, update the
+// running variance with the unbiased one; autograd backward (tools/training/train.py:40).
+#include "tl_common.cuh"
+
+namespace tl {
+namespace train {
+
+constexpr int kMaxCB = 8;   // column blocks of 32: channels <= 256
+
+// per-channel sum and sum of squares of x [n, c] -> acc[0..c) += sum, acc[c..2c) += sumsq (fp64 atomics)
+__global__ void __launch_bounds__(256) k_bn_stats(const float* __restrict__ x, int64_t n, int c, int rows_per_block,
+                                                  double* __restrict__ acc) {
+    __shared__ float red[2][8][32];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+    const int64_t r1 = min(r0 + (int64_t)rows_per_block, n);
+    for (int cb = 0; cb * 32 < c; ++cb) {
+        const int col = cb * 32 + tx;
+        float s = 0.f, q = 0.f;
+        if (col < c)
+            for (int64_t r = r0 + ty; r < r1; r += 8) {
+                const float v = __ldg(x + r * c + col);
+                s += v;
+                q = fmaf(v, v, q);
+            }
+        red[0][ty][tx] = s;
+        red[1][ty][tx] = q;
+        __syncthreads();
+        if (ty == 0 && col < c) {
+            double ds = 0.0, dq = 0.0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) ds += (double)red[0][j][tx], dq += (double)red[1][j][tx];
+            atomicAdd(acc + col, ds);
+            atomicAdd(acc + c + col, dq);
+        }
+        __syncthreads();
+    }
+}
+
+// acc -> mean, invstd, scale = gamma*invstd, shift = beta - mean*scale; running stats momentum update
+__global__ void k_bn_finalize(const double* __restrict__ acc, int64_t n, int c, const float* __restrict__ gamma,
+                              const float* __restrict__ beta, float eps, float momentum, float* running_mean,
+                              float* running_var, float* __restrict__ mean, float* __restrict__ invstd,
+                              float* __restrict__ scale, float* __restrict__ shift) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= c) return;
+    const double m = acc[j] / (double)n;
+    double var = acc[c + j] / (double)n - m * m;   // biased (normalisation)
+    if (var < 0.0) var = 0.0;
+    const float is = (float)(1.0 / sqrt(var + (double)eps));
+    const float g = gamma ? gamma[j] : 1.f, b = beta ? beta[j] : 0.f;
+    mean[j] = (float)m;
+    invstd[j] = is;
+    scale[j] = g * is;
+    shift[j] = b - (float)m * g * is;
+    if (running_mean) running_mean[j] = (1.f - momentum) * running_mean[j] + momentum * (float)m;
+    if (running_var) {
+        const double unbiased = n > 1 ? var * (double)n / (double)(n - 1) : var;
+        running_var[j] = (1.f - momentum) * running_var[j] + momentum * (float)unbiased;
+    }
+}
+
+// out = relu(scale*x + shift)
+__global__ void __launch_bounds__(256) k_bn_relu_apply(const float* __restrict__ x, int64_t total, int c,
+                                                       const float* __restrict__ scale, const float* __restrict__ shift,
+                                                       float* __restrict__ out) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int col = (int)(e % c);
+        out[e] = fmaxf(fmaf(__ldg(x + e), __ldg(scale + col), __ldg(shift + col)), 0.f);
+    }
+}
+
+// dy = d_act * [scale*x+shift > 0]; acc[0..c) += sum dy, acc[c..2c) += sum dy * xhat
+__global__ void __launch_bounds__(256) k_bn_relu_bwd_reduce(const float* __restrict__ x, const float* __restrict__ d_act,
+                                                            int64_t n, int c, int rows_per_block,
+                                                            const float* __restrict__ scale, const float* __restrict__ shift,
+                                                            const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                            double* __restrict__ acc) {
+    __shared__ float red[2][8][32];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+    const int64_t r1 = min(r0 + (int64_t)rows_per_block, n);
+    for (int cb = 0; cb * 32 < c; ++cb) {
+        const int col = cb * 32 + tx;
+        float s = 0.f, q = 0.f;
+        if (col < c) {
+            const float sc = scale[col], sh = shift[col], m = mean[col], is = invstd[col];
+            for (int64_t r = r0 + ty; r < r1; r += 8) {
+                const float v = __ldg(x + r * c + col);
+                const float dy = fmaf(v, sc, sh) > 0.f ? __ldg(d_act + r * c + col) : 0.f;
+                s += dy;
+                q = fmaf(dy, (v - m) * is, q);
+            }
+        }
+        red[0][ty][tx] = s;
+        red[1][ty][tx] = q;
+        __syncthreads();
+        if (ty == 0 && col < c) {
+            double ds = 0.0, dq = 0.0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) ds += (double)red[0][j][tx], dq += (double)red[1][j][tx];
+            atomicAdd(acc + col, ds);
+            atomicAdd(acc + c + col, dq);
+        }
+        __syncthreads();
+    }
+}
+
+// batch-stat mode: dx = scale * (dy - sum_dy/n - xhat * sum_dy_xhat/n); frozen (eval) mode: dx = scale * dy
+__global__ void __launch_bounds__(256) k_bn_relu_bwd_apply(const float* __restrict__ x, const float* __restrict__ d_act,
+                                                           int64_t n, int c, const float* __restrict__ scale,
+                                                           const float* __restrict__ shift, const float* __restrict__ mean,
+                                                           const float* __restrict__ invstd, const double* __restrict__ acc,
+                                                           int batch_stats, float* __restrict__ dx,
+                                                           float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    const int64_t total = n * c;
+    const double inv_n = 1.0 / (double)n;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int col = (int)(e % c);
+        const float v = __ldg(x + e);
+        const float sc = __ldg(scale + col);
+        const float dy = fmaf(v, sc, __ldg(shift + col)) > 0.f ? __ldg(d_act + e) : 0.f;
+        float g = dy;
+        if (batch_stats) {
+            const float xhat = (v - __ldg(mean + col)) * __ldg(invstd + col);
+            g = dy - (float)(acc[col] * inv_n) - xhat * (float)(acc[c + col] * inv_n);
+        }
+        dx[e] = sc * g;
+    }
+    if (blockIdx.x == 0)
+        for (int j = threadIdx.x; j < c; j += blockDim.x) {
+            if (dbeta) dbeta[j] = (float)acc[j];
+            if (dgamma) dgamma[j] = (float)acc[c + j];
+        }
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight gradient: dw[k][ci][co] += sum_r src[index[k][r], ci] * d_out[r, co]
+// One CTA (64 threads, 4x4 register tile each) owns a 32x32 (ci, co) tile of one offset k over a slab of rows;
+// gathered src rows and d_out rows are staged 32 rows at a time in shared memory; partial sums -> fp32 red.add.
+// ------------------------------------------------------------------------------------------------
+constexpr int WG_ROWS = 32;
+
+__global__ void __launch_bounds__(64) k_conv_wgrad(const float* __restrict__ src, int64_t src_stride, int c_in, int n_off,
+                                                   const int32_t* __restrict__ index, int64_t index_stride,
+                                                   const uint32_t* __restrict__ tile_mask, const float* __restrict__ d_out,
+                                                   int64_t n_out, int c_out, int rows_per_block, int co_tiles,
+                                                   float* __restrict__ dw) {
+    __shared__ __align__(16) float xs[WG_ROWS][32];
+    __shared__ __align__(16) float ys[WG_ROWS][32];
+    const int tid = threadIdx.x;
+    const int k = blockIdx.y;
+    const int ci0 = (blockIdx.z / co_tiles) * 32, co0 = (blockIdx.z % co_tiles) * 32;
+    const int ti = tid >> 3, tj = tid & 7;
+    const int64_t r_begin = (int64_t)blockIdx.x * rows_per_block;
+    const int64_t r_end = min(r_begin + (int64_t)rows_per_block, n_out);
+    float acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+    const int lrow = tid >> 3, lc = (tid & 7) * 4;   // loader: 8 rows x 8 float4 per pass, 4 passes
+    for (int64_t rb = r_begin; rb < r_end; rb += WG_ROWS) {
+        if (index && tile_mask && !((tile_mask[rb / TL_TILE_ROWS] >> k) & 1u)) continue;   // block-uniform (rb % 32 == 0)
+        __syncthreads();
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const int rr = p * 8 + lrow;
+            const int64_t r = rb + rr;
+            float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), yv = xv;
+            if (r < r_end) {
+                const int64_t s = index ? (int64_t)__ldg(index + (int64_t)k * index_stride + r) : r;
+                if (s >= 0) {
+                    const float* xp = src + s * src_stride + ci0 + lc;
+                    const float* yp = d_out + r * c_out + co0 + lc;
+                    if (ci0 + lc + 3 < c_in) xv = __ldg(reinterpret_cast<const float4*>(xp));
+                    else {
+                        if (ci0 + lc < c_in) xv.x = __ldg(xp);
+                        if (ci0 + lc + 1 < c_in) xv.y = __ldg(xp + 1);
+                        if (ci0 + lc + 2 < c_in) xv.z = __ldg(xp + 2);
+                    }
+                    if (co0 + lc + 3 < c_out) yv = __ldg(reinterpret_cast<const float4*>(yp));
+                    else {
+                        if (co0 + lc < c_out) yv.x = __ldg(yp);
+                        if (co0 + lc + 1 < c_out) yv.y = __ldg(yp + 1);
+                        if (co0 + lc + 2 < c_out) yv.z = __ldg(yp + 2);
+                    }
+                }
+            }
+            *reinterpret_cast<float4*>(&xs[rr][lc]) = xv;
+            *reinterpret_cast<float4*>(&ys[rr][lc]) = yv;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int rr = 0; rr < WG_ROWS; ++rr) {
+            const float4 a = *reinterpret_cast<const float4*>(&xs[rr][ti * 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&ys[rr][tj * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int v = 0; v < 4; ++v) acc[u][v] = fmaf(av[u], bv[v], acc[u][v]);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int ci = ci0 + ti * 4 + u;
+        if (ci >= c_in) continue;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const int co = co0 + tj * 4 + v;
+            if (co < c_out && acc[u][v] != 0.f) atomicAdd(dw + ((int64_t)k * c_in + ci) * c_out + co, acc[u][v]);
+        }
+    }
+}
+
+static inline int rows_per_block_for(int64_t n, int target_blocks) {
+    int64_t rpb = (n + target_blocks - 1) / target_blocks;
+    rpb = (rpb + 127) / 128 * 128;
+    return (int)(rpb < 128 ? 128 : rpb);
+}
+
+}  // namespace train
+}  // namespace tl
+
+using namespace tl;
+
+extern "C" {
+
+int tl_bn_stats(const float* x, int64_t n, int32_t c, double* acc, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    TL_REQUIRE(x && acc && n > 0 && c > 0 && c <= 32 * train::kMaxCB, "tl_bn_stats: n=%lld c=%d", (long long)n, c);
+    TL_CUDA_CHECK(cudaMemsetAsync(acc, 0, sizeof(double) * 2 * c, stream));
+    const int rpb = train::rows_per_block_for(n, 148 * 8);
+    train::k_bn_stats<<<(unsigned)((n + rpb - 1) / rpb), 256, 0, stream>>>(x, n, c, rpb, acc);
+    TL_LAUNCH_CHECK();
+    return TL_OK;
+}
+
+int tl_bn_finalize(const double* acc, int64_t n, int32_t c, const float* gamma, const float* beta, float eps,
+                   float momentum, float* running_mean, float* running_var, float* mean, float* invstd, float* scale,
+                   float* shift, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    TL_REQUIRE(acc && mean && invstd && scale && shift && n > 0 && c > 0, "tl_bn_finalize: bad arguments");
+    train::k_bn_finalize<<<(c + 127) / 128, 128, 0, stream>>>(acc, n, c, gamma, beta, eps, momentum, running_mean,
+                                                              running_var, mean, invstd, scale, shift);
+    TL_LAUNCH_CHECK();
+    return TL_OK;
+}
+
+int tl_bn_relu_apply(const float* x, int64_t n, int32_t c, const float* scale, const float* shift, float* out,
+                     void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n == 0) return TL_OK;
+    TL_REQUIRE(x && scale && shift && out && c > 0, "tl_bn_relu_apply: bad arguments");
+    const int64_t total = n * c;
+    const unsigned grid = (unsigned)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+    train::k_bn_relu_apply<<<grid, 256, 0, stream>>>(x, total, c, scale, shift, out);
+    TL_LAUNCH_CHECK();
+    return TL_OK;
+}
+
+int tl_bn_relu_bwd(const float* x, const float* d_act, int64_t n, int32_t c, const float* scale, const float* shift,
+                   const float* mean, const float* invstd, int32_t batch_stats, double* acc, float* dx, float* dgamma,
+                   float* dbeta, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n == 0) return TL_OK;
+    TL_REQUIRE(x && d_act && scale && shift && mean && invstd && acc && dx && c > 0 && c <= 32 * train::kMaxCB,
+               "tl_bn_relu_bwd: bad arguments");
+    TL_CUDA_CHECK(cudaMemsetAsync(acc, 0, sizeof(double) * 2 * c, stream));
+    const int rpb = train::rows_per_block_for(n, 148 * 8);
+    train::k_bn_relu_bwd_reduce<<<(unsigned)((n + rpb - 1) / rpb), 256, 0, stream>>>(x, d_act, n, c, rpb, scale, shift,
+                                                                                   mean, invstd, acc);
+    TL_LAUNCH_CHECK();
+    const int64_t total = n * c;
+    const unsigned grid = (unsigned)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+    train::k_bn_relu_bwd_apply<<<grid, 256, 0, stream>>>(x, d_act, n, c, scale, shift, mean, invstd, acc, batch_stats, dx,
+                                                         dgamma, dbeta);
+    TL_LAUNCH_CHECK();
+    return TL_OK;
+}
+
+int tl_conv_wgrad(const float* src, int64_t src_stride, int32_t c_in, int32_t n_off, const int32_t* index,
+                  int64_t index_stride, const uint32_t* tile_mask, const float* d_out, int64_t n_out, int32_t c_out,
+                  float* dw, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    TL_REQUIRE(src && d_out && dw && c_in > 0 && c_out > 0 && n_off >= 1 && n_off <= 27, "tl_conv_wgrad: bad arguments");
+    TL_REQUIRE(index || n_off == 1, "tl_conv_wgrad: identity map needs n_off == 1");
+    TL_REQUIRE(src_stride % 4 == 0 && c_out % 4 == 0, "tl_conv_wgrad: src_stride and c_out must be multiples of 4");
+    TL_CUDA_CHECK(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)n_off * c_in * c_out, stream));
+    if (n_out == 0) return TL_OK;
+    const int ci_tiles = (c_in + 31) / 32, co_tiles = (c_out + 31) / 32;
+    int target = 148 * 24 / (n_off * ci_tiles * co_tiles);
+    if (target < 1) target = 1;
+    const int rpb = train::rows_per_block_for(n_out, target);
+    dim3 grid((unsigned)((n_out + rpb - 1) / rpb), (unsigned)n_off, (unsigned)(ci_tiles * co_tiles));
+    train::k_conv_wgrad<<<grid, 64, 0, stream>>>(src, src_stride, c_in, n_off, index, index_stride, tile_mask, d_out,
+                                                 n_out, c_out, rpb, co_tiles, dw);
+    TL_LAUNCH_CHECK();
+    return TL_OK;
+}
+
+}  // extern "C"

@@ -199,9 +199,6 @@ class TreeLearn(nn.Module):
         return output
 
     def forward_backbone(self, coords, input_feats, batch_ids, batch_size, **kwargs):
-        if self.training and torch.is_grad_enabled():
-            raise NotImplementedError('treelearn_b200: the training (batch-stat BN + backward) path is not built yet; '
-                                      'call under model.eval() / torch.no_grad()')
         dev = torch.device('cuda', torch.cuda.current_device())
         coords, input_feats, batch_ids = (t.to(dev, non_blocking=True) for t in (coords, input_feats, batch_ids))
         vfeats, vcoords, keys, v2p = sparse.voxelize(
@@ -212,7 +209,50 @@ class TreeLearn(nn.Module):
         else:
             shape = (vcoords[:, 1:].max(dim=0).values + 1).tolist()   # reference tree_learn.py:165
         levels = sparse.build_levels(keys, vcoords, shape, self.num_blocks)
+        if self._needs_autograd_path():
+            return self._train_backbone(vfeats, levels), v2p
         return self._run_backbone(vfeats, levels), v2p
+
+    def _needs_autograd_path(self):
+        """The fused inference schedule folds BN running statistics into the conv epilogues and records no graph:
+        it is only valid when no BatchNorm uses batch statistics and no gradient is wanted."""
+        if any(m.training for m in self.modules() if isinstance(m, nn.BatchNorm1d)):
+            return True
+        return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+
+    # ---- training / autograd schedule (unfused: BN batch statistics sit between the convs) ----------
+    def _train_backbone(self, vfeats, levels):
+        from . import autograd as ag
+        mode = _lib.MODE_FP32 if self.mode == 'fp32' else _lib.MODE_TF32
+        geoms = {'subm': [ag.subm_geom(lv) for lv in levels],
+                 'down': [ag.down_geom(levels[l], levels[l + 1]) for l in range(len(levels) - 1)],
+                 'up': [ag.up_geom(levels[l], levels[l + 1]) for l in range(len(levels) - 1)]}
+        x = ag.sparse_conv(vfeats, self._get('input_conv.0').weight, geoms['subm'][0], mode)
+        x = self._train_ublock('unet', 0, x, geoms, mode)
+        return ag.bn_relu(x, self._get('output_layer.0'))
+
+    def _train_residual(self, p, x, geom, mode):
+        from . import autograd as ag
+        h = ag.sparse_conv(ag.bn_relu(x, self._get(p + '.conv_branch.0')), self._get(p + '.conv_branch.2').weight, geom, mode)
+        h = ag.sparse_conv(ag.bn_relu(h, self._get(p + '.conv_branch.3')), self._get(p + '.conv_branch.5').weight, geom, mode)
+        blk = self._get(p)
+        if 'i_branch' in blk._modules:   # 1x1 projection of the residual branch (reference blocks.py:29-39)
+            x = ag.sparse_conv(x, self._get(p + '.i_branch.0').weight, ag.identity_geom(x.shape[0]), mode)
+        return h + x
+
+    def _train_ublock(self, p, l, x, geoms, mode):
+        from . import autograd as ag
+        g = geoms['subm'][l]
+        for i in range(2):
+            x = self._train_residual(f'{p}.blocks.block{i}', x, g, mode)
+        if l + 1 < self.num_blocks:
+            d = ag.sparse_conv(ag.bn_relu(x, self._get(p + '.conv.0')), self._get(p + '.conv.2').weight, geoms['down'][l], mode)
+            d = self._train_ublock(p + '.u', l + 1, d, geoms, mode)
+            up = ag.sparse_conv(ag.bn_relu(d, self._get(p + '.deconv.0')), self._get(p + '.deconv.2').weight, geoms['up'][l], mode)
+            x = torch.cat([x, up], dim=1)
+            for i in range(2):
+                x = self._train_residual(f'{p}.blocks_tail.block{i}', x, g, mode)
+        return x
 
     def _run_backbone(self, vfeats, levels):
         pk = self._pack()
@@ -256,6 +296,11 @@ class TreeLearn(nn.Module):
         return conv([nbr(ha, pk[t1 + '.5'][0])], residual=t, act1=ret_act)
 
     def forward_head(self, voxel_out, v2p):
+        if voxel_out.requires_grad or self.semantic_linear[1].training or self.offset_linear[1].training:
+            # training: gather + the two tiny MLPs as torch ops so autograd and batch-stat BN apply (tree_learn.py:97-103)
+            feats = voxel_out.float()[v2p]
+            return {'backbone_feats': feats, 'semantic_prediction_logits': self.semantic_linear(feats),
+                    'offset_predictions': self.offset_linear(feats)}
         feats, logits, offs = sparse.heads(voxel_out, v2p, self._pack())
         return {'backbone_feats': feats, 'semantic_prediction_logits': logits, 'offset_predictions': offs}
 
