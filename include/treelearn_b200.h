@@ -71,7 +71,9 @@ int tl_subm_rulebook(const uint64_t* keys, int64_t n, const int32_t* spatial_sha
  *   acc[r,:] = sum_seg sum_k W_seg[k] . src_seg[index_seg[k][r], :]     (index NULL => identity, n_off==1)
  *   v = acc + residual[r,:]
  *   out_raw = v ; out_act1 = relu(scale1*v+shift1) ; out_act2 = relu(scale2*v+shift2)   (each optional)
- * weight layout: mode 0 (fp32 SIMT) [n_off][c_in][c_out]; modes 1/2 (tcgen05 tf32 / f16) [n_off][c_out][c_in]. */
+ * weight layout: mode 0 (fp32 SIMT) [n_off][c_in][c_out]; modes 1/2 (tcgen05 tf32 / f16) [n_off][c_in/32][c_out][32]
+ * with the 16 B chunks of every 32-channel row XOR-swizzled by the row index (c ^ (n & 7) for 128 B tf32 rows,
+ * c ^ ((n >> 1) & 3) for 64 B fp16 rows) = the UMMA shared-memory B-operand image (treelearn_b200/sparse.py::pack_weight_tc). */
 typedef struct {
     const float* src;
     int64_t src_stride; /* floats per row */

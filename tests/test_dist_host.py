@@ -5,7 +5,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from treelearn_b200.dist import allgather_rows, shard_indices
+from treelearn_b200.dist import allgather_rows, allreduce_grads, grad_buckets, shard_indices
 
 
 def test_shard_indices_is_a_balanced_partition():
@@ -44,3 +44,49 @@ def test_allgather_rows_gloo_world2():
     for rank, out, n_empty in res:
         assert out == expect            # identical on both ranks, rank order preserved
         assert n_empty == 7
+
+
+def _grad_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from treelearn_b200 import TreeLearn
+    torch.manual_seed(0)
+    net = TreeLearn(channels=8, num_blocks=3, fixed_modules=['semantic_linear'])
+    for i, p in enumerate(net.parameters()):
+        if p.requires_grad and i % 5 != 0:                       # leave some grads None: treated as zeros
+            p.grad = torch.full_like(p, float(rank + 1) * (1 + i % 3))
+    allreduce_grads(net)
+    ok = True
+    for i, p in enumerate(net.parameters()):
+        if not p.requires_grad:
+            ok &= p.grad is None
+        elif i % 5 != 0:
+            ok &= bool(torch.allclose(p.grad, torch.full_like(p, 1.5 * (1 + i % 3))))    # mean of ranks {1,2} x factor
+        else:
+            ok &= bool((p.grad == 0).all())
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_allreduce_grads_gloo_world2():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == [(0, True), (1, True)]
+
+
+def test_grad_buckets_cover_trainable_parameters_once():
+    from treelearn_b200 import TreeLearn
+    net = TreeLearn(channels=8, num_blocks=4, fixed_modules=['offset_linear'])
+    buckets = grad_buckets(net)
+    flat = [id(p) for b in buckets for p in b]
+    want = [id(p) for p in net.parameters() if p.requires_grad]
+    assert sorted(flat) == sorted(want) and len(set(flat)) == len(flat)
+    assert len(buckets) == 5                                   # 4 U-Net levels + the non-U-Net bucket

@@ -261,7 +261,7 @@ TF32_EXACT_TOL = dict(atol=3e-4, rtol=2e-4)    # operands pre-rounded to TF32: o
 
 
 def _tc_weight(w, co, k, ci):
-    return _round_tf32(w.reshape(co, k, ci).permute(1, 0, 2).contiguous()).cuda()
+    return sparse.pack_weight_tc(w.reshape(co, k, ci).permute(1, 0, 2).cuda(), False)
 
 
 @pytest.mark.parametrize('ci,co', [(32, 32), (64, 32), (32, 64), (96, 96), (128, 160), (224, 224)])
@@ -358,7 +358,7 @@ def test_f16_subm_conv_parity(ci, co):
     res = torch.randn((lv.n, co), generator=g)
     s, t = torch.rand(co, generator=g) + 0.5, torch.randn(co, generator=g)
     ref = model_ref._subm(x.float(), sp.subm_neighbour_table(vc.cpu().numpy(), [500, 500, 1000]), w.float()) + res
-    wp = w.reshape(co, 27, ci).permute(1, 0, 2).contiguous().cuda()
+    wp = sparse.pack_weight_tc(w.reshape(co, 27, ci).permute(1, 0, 2).cuda(), True)
     raw, act = sparse.conv([sparse.Seg(x.cuda(), wp, lv.nbr, lv.nbr_mask)], lv.n, co, _lib.MODE_F16,
                            residual=res.cuda(), raw=True, act1=(s.cuda(), t.cuda()))
     assert raw.dtype == torch.float32 and act.dtype == torch.float16

@@ -10,11 +10,12 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from treelearn_b200 import TreeLearn, synth, sparse, pipeline  # noqa: E402
 
 workload = sys.argv[1] if len(sys.argv) > 1 else 'cfg2_2M'
-mode = sys.argv[2] if len(sys.argv) > 2 else 'tf32'
+mode = sys.argv[2] if len(sys.argv) > 2 else 'f16'
 G = SimpleNamespace(tree_conf_thresh=0.5, tau_vert=0.6, tau_off=4, tau_group=0.15, tau_min=50, use_hdbscan=False)
 shape = [1000, 1000, 1000]
 batch = synth.make_batch([synth.workload(workload)])
 dev = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in batch.items() if k in ('coords', 'input_feats', 'batch_ids', 'batch_size')}
+torch.manual_seed(0)   # same random-init network as bench.py
 net = synth.randomize_bn_stats(TreeLearn(use_feats=False, use_coords=False, spatial_shape=shape, mode=mode)).cuda().eval()
 
 

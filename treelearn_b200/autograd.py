@@ -63,7 +63,7 @@ def _round_tf32(w):
 def _pack(w_kco_ci, c_in, c_out, mode):
     """w [K, C_out, C_in] (K-major B operand) -> the layout tl_conv_fwd wants for (mode, shape); returns (w, mode)."""
     if mode != _lib.MODE_FP32 and _tc_ok(c_in, c_out):
-        return _round_tf32(w_kco_ci.contiguous()), _lib.MODE_TF32
+        return sparse.pack_weight_tc(w_kco_ci, False), _lib.MODE_TF32
     return w_kco_ci.permute(0, 2, 1).contiguous(), _lib.MODE_FP32      # SIMT layout [K, C_in, C_out]
 
 

@@ -260,29 +260,83 @@ __global__ void k_cc_labels(const int* __restrict__ root, const int* __restrict_
 // ------------------------------------------------------------------------------------------------
 // kNN majority vote over a 3-D cell grid, expanding cube search + exact brute-force fallback
 // ------------------------------------------------------------------------------------------------
+// kNN vote.  One cell-sort serves three grid resolutions: the 48-bit key of a reference point is hierarchical,
+//   [ 12-bit 4 m cell x,y,z | 2-bit 1 m sub-cell x,y,z | 2-bit 0.25 m sub-cell x,y,z ],
+// so points sorted by it are grouped by 0.25 m cell, by 1 m cell (key >> 6) and by 4 m cell (key >> 12) at once;
+// each level only adds a (cell prefix -> [first, last) row) hash table.
+// ------------------------------------------------------------------------------------------------
 constexpr int kMaxK = 8;
-constexpr int kMaxRing = 6;
+constexpr int kKnnLevels = 3;
+constexpr double kKnnCell0 = 0.25;      // level l cells are 0.25 * 4^l m
+constexpr int kFineBits = 16;           // fine (0.25 m) cell index bits per axis (+-8 km around the origin)
+constexpr int kFineBias = 1 << (kFineBits - 1);
+
+__device__ __forceinline__ int knn_fine_index(float v) {
+    int64_t c = (int64_t)floor((double)v * (1.0 / kKnnCell0)) + kFineBias;
+    return (int)(c < 8 ? 8 : (c > (1 << kFineBits) - 9 ? (1 << kFineBits) - 9 : c));   // clamp, leaving room for the rings
+}
+// prefix key of the level-l cell with (biased) level-l cell indices (cx,cy,cz)
+__device__ __forceinline__ uint64_t knn_prefix(int cx, int cy, int cz, int level) {
+    uint64_t key = 0;
+    const int top = kFineBits - 2 * level;     // bits per axis at this level
+    const int coarse = top - 2 * (2 - level);  // bits of the 4 m part
+    key = ((uint64_t)(cx >> (top - coarse)) << (2 * coarse)) | ((uint64_t)(cy >> (top - coarse)) << coarse) |
+          (uint64_t)(cz >> (top - coarse));
+    for (int sub = 2 - level - 1; sub >= 0; --sub)   // 2-bit digits below the 4 m part, most significant first
+        key = (key << 6) | ((uint64_t)((cx >> (2 * sub)) & 3) << 4) | ((uint64_t)((cy >> (2 * sub)) & 3) << 2) |
+              (uint64_t)((cz >> (2 * sub)) & 3);
+    return key;
+}
+
+__global__ void k_knn_keys(const float* __restrict__ pts, int64_t n, uint64_t* __restrict__ keys, int* __restrict__ idx) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    keys[i] = knn_prefix(knn_fine_index(pts[i * 3]), knn_fine_index(pts[i * 3 + 1]), knn_fine_index(pts[i * 3 + 2]), 0);
+    idx[i] = (int)i;
+}
+
+// cell-sorted coordinate copy with the original reference index in .w
+__global__ void k_knn_gather(const int* __restrict__ sidx, int64_t n, const float* __restrict__ pts,
+                             float4* __restrict__ spts) {
+    int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const int i = sidx[j];
+    spts[j] = make_float4(pts[(int64_t)i * 3], pts[(int64_t)i * 3 + 1], pts[(int64_t)i * 3 + 2], __int_as_float(i));
+}
+
+// level table: first row of every run of equal (key >> shift); the run ends where the next run starts
+__global__ void k_knn_table(const uint64_t* __restrict__ skeys, int64_t n, int shift, uint64_t* tkeys, int* tvals,
+                            uint64_t mask) {
+    int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const uint64_t key = skeys[j] >> shift;
+    if (j == 0 || (skeys[j - 1] >> shift) != key) hash_insert(tkeys, tvals, mask, key, (int)j);
+}
 
 struct TopK {
     double d[kMaxK];
-    int64_t lab[kMaxK];
     int idx[kMaxK];
     int k;
+    float worst_f;   // fp32 upper bound of d[k-1] (pre-filter threshold), kept in a register
     __device__ void init(int k_) {
         k = k_;
-        for (int t = 0; t < kMaxK; ++t) d[t] = 1e300, lab[t] = 0, idx[t] = 0x7fffffff;
+        for (int t = 0; t < kMaxK; ++t) d[t] = 1e300, idx[t] = 0x7fffffff;
+        worst_f = __int_as_float(0x7f800000);
     }
     // ordered by (distance, reference index): deterministic under ties
-    __device__ void push(double dist, int64_t label, int index) {
+    __device__ void push(double dist, int index) {
         if (dist > d[k - 1] || (dist == d[k - 1] && index >= idx[k - 1])) return;
         int t = k - 1;
         while (t > 0 && (d[t - 1] > dist || (d[t - 1] == dist && idx[t - 1] > index))) {
-            d[t] = d[t - 1], lab[t] = lab[t - 1], idx[t] = idx[t - 1];
+            d[t] = d[t - 1], idx[t] = idx[t - 1];
             --t;
         }
-        d[t] = dist, lab[t] = label, idx[t] = index;
+        d[t] = dist, idx[t] = index;
+        worst_f = (float)d[k - 1] * 1.00001f + 1e-30f;
     }
-    __device__ int64_t vote() const {  // most frequent label, ties -> smallest label
+    __device__ int64_t vote(const int64_t* __restrict__ labels) const {  // most frequent label, ties -> smallest label
+        int64_t lab[kMaxK];
+        for (int a = 0; a < k; ++a) lab[a] = labels[idx[a]];
         int64_t best = 0;
         int best_cnt = 0;
         for (int a = 0; a < k; ++a) {
@@ -294,58 +348,80 @@ struct TopK {
     }
 };
 
-struct GridView {
+struct KnnLevel {
     const uint64_t* tkeys;
     const int* tvals;
     uint64_t mask;
-    const int* seg_start;
-    const int* sidx;
-    const float* spts;
-    double cell;
+    int shift;      // key >> shift = this level's cell prefix
     int max_ring;
 };
 
+struct KnnGrid {
+    const uint64_t* skeys;   // sorted hierarchical keys
+    const float4* spts;      // cell-sorted (x, y, z, original index)
+    int64_t n;
+    KnnLevel level[kKnnLevels];
+};
+
+__device__ __forceinline__ void knn_scan_cell(const KnnGrid& g, const KnnLevel& lv, uint64_t prefix, float qx, float qy,
+                                              float qz, TopK& top) {
+    int j = hash_find(lv.tkeys, lv.tvals, lv.mask, prefix);
+    if (j < 0) return;
+    const double x = qx, y = qy, z = qz;
+    for (; j < g.n; ++j) {
+        if (lv.shift ? ((__ldg(g.skeys + j) >> lv.shift) != prefix) : (__ldg(g.skeys + j) != prefix)) break;
+        const float4 p = __ldg(g.spts + j);
+        // fp32 pre-filter (relative error of the fp32 sum of squares << 1e-5), then the exact fp64 distance
+        const float fx = qx - p.x, fy = qy - p.y, fz = qz - p.z;
+        const float d2f = fx * fx + fy * fy + fz * fz;
+        if (d2f > top.worst_f) continue;
+        const double ax = x - (double)p.x, ay = y - (double)p.y, az = z - (double)p.z;
+        const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)), __dmul_rn(az, az));
+        top.push(d2, __float_as_int(p.w));
+    }
+}
+
 // Multi-resolution search: level 0 has small cells (dense tree-base blobs after the offset shift), coarser levels catch
 // sparse neighbourhoods without probing hundreds of empty cells; exact scan of all references as the last resort.
-// A level's result is final once the k-th distance is within the radius that level has provably covered.
-__global__ void k_knn_vote(const float* __restrict__ query, int64_t nq, GridView g0, GridView g1, GridView g2,
-                           const int64_t* __restrict__ ref_labels, int64_t n_ref, int k, int64_t* __restrict__ out) {
+// Within a level the rings are scanned shell by shell (nothing is re-read); a level's result is final once the k-th
+// distance is within the radius that level has provably covered.
+__global__ void __launch_bounds__(128) k_knn_vote(const float* __restrict__ query, int64_t nq, const KnnGrid g,
+                                                  const int64_t* __restrict__ ref_labels, int k,
+                                                  int64_t* __restrict__ out) {
     int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (q >= nq) return;
-    const double x = query[q * 3], y = query[q * 3 + 1], z = query[q * 3 + 2];
+    const float qx = query[q * 3], qy = query[q * 3 + 1], qz = query[q * 3 + 2];
+    const int fx = knn_fine_index(qx), fy = knn_fine_index(qy), fz = knn_fine_index(qz);
     TopK top;
     bool done = false;
-    for (int level = 0; level < 3 && !done; ++level) {
-        const GridView& g = level == 0 ? g0 : (level == 1 ? g1 : g2);
-        const int64_t cx = (int64_t)floor(x / g.cell), cy = (int64_t)floor(y / g.cell), cz = (int64_t)floor(z / g.cell);
-        for (int ring = 1; ring <= g.max_ring && !done; ++ring) {
-            top.init(k);
+    for (int level = 0; level < kKnnLevels && !done; ++level) {
+        const KnnLevel& lv = g.level[level];
+        const int cx = fx >> (2 * level), cy = fy >> (2 * level), cz = fz >> (2 * level);
+        const double cell = kKnnCell0 * (double)(1 << (2 * level));
+        top.init(k);
+        for (int ring = 0; ring <= lv.max_ring && !done; ++ring) {
             for (int dx = -ring; dx <= ring; ++dx)
-                for (int dy = -ring; dy <= ring; ++dy)
-                    for (int dz = -ring; dz <= ring; ++dz) {
-                        const int seg = hash_find(g.tkeys, g.tvals, g.mask, cell_key3(cx + dx, cy + dy, cz + dz));
-                        if (seg < 0) continue;
-                        for (int j = g.seg_start[seg]; j < g.seg_start[seg + 1]; ++j) {
-                            const double ax = x - (double)g.spts[j * 3], ay = y - (double)g.spts[j * 3 + 1],
-                                         az = z - (double)g.spts[j * 3 + 2];
-                            const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)), __dmul_rn(az, az));
-                            top.push(d2, ref_labels[g.sidx[j]], g.sidx[j]);
-                        }
-                    }
+                for (int dy = -ring; dy <= ring; ++dy) {
+                    const bool edge = (dx == -ring || dx == ring || dy == -ring || dy == ring);
+                    for (int dz = -ring; dz <= ring; dz += (edge || ring == 0) ? 1 : 2 * ring)   // shell cells only
+                        knn_scan_cell(g, lv, knn_prefix(cx + dx, cy + dy, cz + dz, level), qx, qy, qz, top);
+                }
             // every reference closer than ring*cell was seen (the query lies inside the centre cell)
-            const double safe = (double)ring * g.cell;
-            done = top.d[k - 1] <= safe * safe;
+            const double safe = (double)ring * cell;
+            done = ring > 0 && top.d[k - 1] <= safe * safe;
         }
     }
     if (!done) {  // farther than every grid reaches: exact scan of all references (rare)
         top.init(k);
-        for (int64_t j = 0; j < n_ref; ++j) {
-            const double ax = x - (double)g0.spts[j * 3], ay = y - (double)g0.spts[j * 3 + 1], az = z - (double)g0.spts[j * 3 + 2];
+        const double x = qx, y = qy, z = qz;
+        for (int64_t j = 0; j < g.n; ++j) {
+            const float4 p = __ldg(g.spts + j);
+            const double ax = x - (double)p.x, ay = y - (double)p.y, az = z - (double)p.z;
             const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)), __dmul_rn(az, az));
-            top.push(d2, ref_labels[g0.sidx[j]], g0.sidx[j]);
+            top.push(d2, __float_as_int(p.w));
         }
     }
-    out[q] = top.vote();
+    out[q] = top.vote(ref_labels);
 }
 
 }  // namespace tl
@@ -451,7 +527,12 @@ int tl_cluster_radius_cc(const float* points_xy, int64_t n, double radius, int64
 size_t tl_knn_workspace_bytes(int64_t n_ref, int64_t n_query) {
     (void)n_query;
     if (n_ref <= 0) return 256;
-    return 3 * (grid_bytes(n_ref) + 1024);
+    const uint64_t cap = table_capacity(n_ref);
+    size_t cub_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (uint64_t*)nullptr, (uint64_t*)nullptr, (int*)nullptr, (int*)nullptr,
+                                    (int)n_ref);
+    return 2 * align_up(n_ref * 8) + 2 * align_up(n_ref * 4) + align_up(n_ref * 16) +
+           kKnnLevels * (align_up(cap * 8) + align_up(cap * 4)) + align_up(cub_bytes) + 4096;
 }
 
 int tl_knn_vote(const float* ref_xyz, const int64_t* ref_labels, int64_t n_ref, const float* query_xyz, int64_t n_query,
@@ -461,18 +542,38 @@ int tl_knn_vote(const float* ref_xyz, const int64_t* ref_labels, int64_t n_ref, 
     TL_REQUIRE(k >= 1 && k <= kMaxK, "tl_knn_vote: k=%d (1..%d)", k, kMaxK);
     TL_REQUIRE(n_ref >= k && n_ref < (1ll << 31), "tl_knn_vote: n_ref=%lld must be >= k=%d", (long long)n_ref, k);
     Carver c(workspace, workspace_bytes);
-    const double cells[3] = {0.25, 1.0, 4.0};
-    const int rings[3] = {2, 3, 4};
-    GridView gv[3];
-    for (int l = 0; l < 3; ++l) {
-        CellGrid g;
-        TL_REQUIRE(carve_grid(c, n_ref, g), "tl_knn_vote: workspace too small");
-        int rc = build_grid<3>(ref_xyz, n_ref, cells[l], g, stream);
-        if (rc != TL_OK) return rc;
-        gv[l] = GridView{g.tkeys, g.tvals, g.cap - 1, g.seg_start, g.idx_out, g.spts, cells[l], rings[l]};
+    uint64_t* keys_in = c.take<uint64_t>(n_ref);
+    uint64_t* keys_out = c.take<uint64_t>(n_ref);
+    int* idx_in = c.take<int>(n_ref);
+    int* idx_out = c.take<int>(n_ref);
+    float4* spts = c.take<float4>(n_ref);
+    const uint64_t cap = table_capacity(n_ref);
+    uint64_t* tkeys[kKnnLevels];
+    int* tvals[kKnnLevels];
+    for (int l = 0; l < kKnnLevels; ++l) tkeys[l] = c.take<uint64_t>(cap), tvals[l] = c.take<int>(cap);
+    size_t cub_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (uint64_t*)nullptr, (uint64_t*)nullptr, (int*)nullptr, (int*)nullptr,
+                                    (int)n_ref);
+    void* cub_tmp = c.take<char>(cub_bytes);
+    TL_REQUIRE(c.ok(), "tl_knn_vote: workspace too small");
+    const int T = 256;
+    const unsigned nb = (unsigned)((n_ref + T - 1) / T);
+    k_knn_keys<<<nb, T, 0, stream>>>(ref_xyz, n_ref, keys_in, idx_in);
+    TL_LAUNCH_CHECK();
+    TL_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, keys_in, keys_out, idx_in, idx_out, (int)n_ref, 0,
+                                                  3 * kFineBits, stream));
+    k_knn_gather<<<nb, T, 0, stream>>>(idx_out, n_ref, ref_xyz, spts);
+    TL_LAUNCH_CHECK();
+    const int rings[kKnnLevels] = {2, 3, 4};
+    KnnGrid g;
+    g.skeys = keys_out, g.spts = spts, g.n = n_ref;
+    for (int l = 0; l < kKnnLevels; ++l) {
+        TL_CUDA_CHECK(cudaMemsetAsync(tkeys[l], 0xFF, cap * 8, stream));
+        k_knn_table<<<nb, T, 0, stream>>>(keys_out, n_ref, 6 * l, tkeys[l], tvals[l], cap - 1);
+        TL_LAUNCH_CHECK();
+        g.level[l] = KnnLevel{tkeys[l], tvals[l], cap - 1, 6 * l, rings[l]};
     }
-    k_knn_vote<<<(unsigned)((n_query + 127) / 128), 128, 0, stream>>>(query_xyz, n_query, gv[0], gv[1], gv[2], ref_labels,
-                                                                      n_ref, k, out_labels);
+    k_knn_vote<<<(unsigned)((n_query + 127) / 128), 128, 0, stream>>>(query_xyz, n_query, g, ref_labels, k, out_labels);
     TL_LAUNCH_CHECK();
     return TL_OK;
 }

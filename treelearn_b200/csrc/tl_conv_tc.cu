@@ -1,23 +1,23 @@
-// tcgen05 / TMEM segmented gather-GEMM sparse convolution (mode TL_MODE_TF32), sm_100a only.
+// tcgen05 / TMEM segmented gather-GEMM sparse convolution (modes TL_MODE_TF32 / TL_MODE_F16), sm_100a only.
 //
 // One CTA owns a tile of 128 output voxels (UMMA M=128, cta_group::1) and all C_out columns
 // (UMMA N = C_out, fp32 accumulators in TMEM, double-buffered so the epilogue of tile i overlaps the
-// main loop of tile i+1).  The K loop runs over (segment, kernel offset, 32-channel block): per step
-//   * 4 producer warps gather the 128 neighbour rows (128 B each, cp.async 16 B through L1, zero-fill for
-//     absent neighbours) into a 128B-swizzled K-major A stage and copy the offset's [C_out x 32] weight slab
-//     into a B stage -- exactly the canonical SWIZZLE_128B layouts the UMMA shared-memory descriptors name.
-//     The ring is deep (S stages, S-2 cp.async groups in flight per thread): the gather is latency bound.
-//   * 1 MMA thread issues 4 x tcgen05.mma.kind::tf32 (K=8 each) and tcgen05.commit's the stage back;
-//   * 4 epilogue warps tcgen05.ld the accumulator rows, add the residual, and write up to three outputs
-//     (raw, and relu(scale*v+shift) for the next layers' BatchNorm+ReLU, rounded to TF32 so the tensor
-//     core's operand truncation of those tensors is exact).
+// main loop of tile i+1).  The K loop runs over (segment, kernel offset, 32-channel block) "chunks"; per chunk
+//   * 4 producer warps gather the 128 neighbour rows (one 64 B / 128 B swizzle row each; cp.async.cg 16 B, absent
+//     neighbours read a global zero row so every copy is a uniform 16 B) into a swizzled K-major A stage;
+//   * one weight-loader thread lands the chunk's [C_out x 32] weight slab in the B stage with a single TMA bulk copy
+//     (weights are packed per slab with the shared-memory swizzle already applied: sparse.pack_weight_tc);
+//     both complete on the stage's mbarrier (cp.async noinc arrivals + expect_tx bytes);
+//   * 1 MMA thread issues the tcgen05.mma K steps (kind::tf32 K=8 / kind::f16 K=16) and tcgen05.commit's the stage back;
+//   * 4 epilogue warps tcgen05.ld the accumulator rows, transpose them through a per-warp shared-memory tile so that
+//     all global traffic is full 128 B lines, add the residual and write up to three outputs (raw fp32, and
+//     relu(scale*v+shift) for the next layers' BatchNorm+ReLU in the consumers' operand format: TF32-rounded fp32 or fp16).
 // Offsets that no voxel of the tile uses are skipped through the rulebook's per-tile bitmask.
-// Layers with few tiles (deep U-Net levels: big weights, few voxels) run split-K: the (offset, k-block) range of a
-// tile is divided over several CTAs which red.add their partial accumulators into a zeroed fp32 buffer; a small
-// elementwise kernel then applies residual / BN / ReLU.
-// Shared memory is kept near 128 KB so that ~96 KB of L1 remains: the ~14x re-read of neighbour rows inside a
-// Morton-ordered tile is served by L1, not L2.
-// Weights arrive pre-rounded (RN) to TF32, layout [n_off][C_out][C_in] (K-major B operand).
+// Layers with few tiles (deep U-Net levels: big weights, few voxels) run split-K: the chunk range of a tile is divided
+// over several CTAs which red.add their partial accumulators into a zeroed fp32 buffer; a small elementwise kernel
+// then applies residual / BN / ReLU.
+// Measured limits that shaped this (profiles/r01_ncu_full_k_conv_tc_s2.txt): the LSU data pipe (cp.async shared-memory
+// writes + uncoalesced epilogue accesses) was 72 % busy and the producer loop issued 178 instructions per chunk.
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
@@ -29,18 +29,20 @@ namespace tc {
 constexpr int BM = 128;          // rows per tile == TMEM lanes
 constexpr int BK = 32;           // channels per K block: one swizzle row of 128 B (fp32/TF32 operands) or 64 B (fp16)
 constexpr int MAX_STAGES = 12;
-constexpr int A_STAGE_BYTES = BM * 128;   // fp32 operands (largest case; used for sizing)
 constexpr int kMaxGroups = 4;            // producer groups of four warps; group g fills the chunks with ordinal % G == g
 constexpr int kProducerWarps = 4 * kMaxGroups;
-constexpr int kProducerThreads = 128;    // arrivals per stage (one group)
+constexpr int kProducerThreads = 128;    // cp.async arrivals per stage (one group); +1 arrival from the weight loader
 constexpr int kEpilogueThreads = 128;
 constexpr int kFirstEpilogueWarp = kProducerWarps;      // 16..19: warp % 4 == TMEM lane quarter
 constexpr int kMmaWarp = kProducerWarps + 4;            // 20
 constexpr int kSchedWarp = kProducerWarps + 5;          // 21: builds each work item's descriptor (rulebook rows + chunk list)
-constexpr int kThreads = 32 * (kProducerWarps + 4 + 2);
+constexpr int kWeightWarp = kProducerWarps + 6;         // 22: one thread bulk-copies (TMA) each chunk's weight slab
+constexpr int kThreads = 32 * (kProducerWarps + 4 + 3);
 constexpr int MAX_CHUNKS = 448;                         // live (segment, offset, k-block) entries per work item
 constexpr int IDX_ROWS = 32;                         // rulebook rows (segment, offset) staged per tile
 constexpr int IDX_BUF_BYTES = IDX_ROWS * BM * 4 + MAX_CHUNKS * 4 + 64;   // rulebook rows + chunk list + count; x2
+constexpr int EPI_BYTES = 4 * 32 * 128;              // per epilogue warp: 32 rows x 32 fp32 columns, transposed for coalescing
+constexpr int SEGTAB_BYTES = 32 * TL_MAX_SEG;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -188,35 +190,87 @@ __device__ __forceinline__ void store_act32(void* out, int64_t elem_off, const f
         }
     }
 }
+// 4 consecutive activated columns -> the consumer's operand format (16 B of TF32-rounded fp32 or 8 B of fp16)
+template <int EB>
+__device__ __forceinline__ void store_act4(void* out, int64_t e, float a0, float a1, float a2, float a3) {
+    if (EB == 4) {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + e) =
+            make_float4(round_tf32(a0), round_tf32(a1), round_tf32(a2), round_tf32(a3));
+    } else {
+        const __half2 h0 = __floats2half2_rn(a0, a1), h1 = __floats2half2_rn(a2, a3);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(out) + e) =
+            make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+    }
+}
 template <int EB>
 __device__ __forceinline__ void store_act1(void* out, int64_t e, float a) {
     if (EB == 4) reinterpret_cast<float*>(out)[e] = round_tf32(a);
     else reinterpret_cast<__half*>(out)[e] = __float2half_rn(a);
 }
 
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// TMA bulk copy global -> shared, completion (bytes) signalled on the mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint2 ld_shared_u2(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+
+// one lane of a converged warp (cute::elect_one_sync): keeps the surrounding loop warp-uniform, so the compiler holds
+// descriptors / barrier addresses in uniform registers instead of wrapping every tcgen05 / bulk-copy instruction in a
+// per-lane "waterfall" loop (measured: ~375 issue cycles per chunk in the old `if (lane == 0)` MMA loop)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n"
+        ".reg .b32 rx;\n"
+        ".reg .pred px;\n"
+        "elect.sync rx|px, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, px;\n"
+        "}\n"
+        : "=r"(pred)::"memory");
+    return pred != 0;
+}
+
 struct Launch {   // per-launch scalars (kernel parameter)
     int num_tiles;     // row tiles
     int splits;        // CTAs sharing one tile's K range (1 = fused epilogue)
     int chunks_total;  // (segment, offset, k-block) ordinals per tile, masked ones included
-    int stages, lag;
+    int stages;        // ring slots; every slot holds `q` chunks (sub-stages) handed over with ONE barrier round trip
+    int q;
     int tmem_cols, buf_cols;   // TMEM columns allocated / per accumulator buffer (two buffers)
     int debug;                 // timing experiments only: 1 = skip MMAs, 2 = skip A gather, 4 = skip epilogue memory ops, 8 = skip B copy
     int acc_ways, acc_cols;    // independent accumulators per buffer (K-step kk -> accumulator kk % ways) and their stride
     float* splitk_ws;  // [n_out, c_out] zeroed fp32 accumulation buffer when splits > 1
     int groups;        // active producer groups (power of two <= kMaxGroups, < stages)
     int use_cg;        // gather A rows with cp.async.cg (bypass L1) instead of .ca
-    int idx_base[TL_MAX_SEG];   // first prefetch row of each indexed segment (segments sharing a table share rows)
+    int idx_base[TL_MAX_SEG];   // first prefetch row of each indexed segment (segments sharing a table share rows); -1 = identity
     int idx_owner[TL_MAX_SEG];  // 1 = this segment's table rows are fetched (0 = alias of an earlier segment)
 };
 
 struct Layout {  // dynamic shared memory carve-up (1024 B aligned base)
     uint32_t a0, b0, a_stage_bytes, b_stage_bytes;
-    uint32_t full0, empty0, tfull0, tempty0, tmem_slot, idx0;
+    uint32_t full0, empty0, tfull0, tempty0, tmem_slot, idx0, epi0, segtab;
     __device__ __forceinline__ uint32_t idx(uint32_t buf, int row, int col) const {
         return idx0 + buf * IDX_BUF_BYTES + (uint32_t)(row * BM + col) * 4u;
     }
-    __device__ __forceinline__ uint32_t a(uint32_t s) const { return a0 + s * a_stage_bytes; }
-    __device__ __forceinline__ uint32_t b(uint32_t s) const { return b0 + s * b_stage_bytes; }
+    __device__ __forceinline__ uint32_t a(uint32_t sub) const { return a0 + sub * a_stage_bytes; }   // sub = slot * q + i
+    __device__ __forceinline__ uint32_t b(uint32_t sub) const { return b0 + sub * b_stage_bytes; }
     __device__ __forceinline__ uint32_t full(uint32_t s) const { return full0 + 8 * s; }
     __device__ __forceinline__ uint32_t empty(uint32_t s) const { return empty0 + 8 * s; }
     __device__ __forceinline__ uint32_t tfull(uint32_t b) const { return tfull0 + 8 * b; }
@@ -231,23 +285,26 @@ struct Layout {  // dynamic shared memory carve-up (1024 B aligned base)
     }
 };
 
-__device__ __forceinline__ Layout carve(uint32_t base, int n, int stages, int row_bytes) {
+__device__ __forceinline__ Layout carve(uint32_t base, int n, int substages, int row_bytes) {
     Layout L;
     L.a0 = base;
     L.a_stage_bytes = BM * row_bytes;
-    L.b0 = base + stages * L.a_stage_bytes;
+    L.b0 = base + substages * L.a_stage_bytes;
     L.b_stage_bytes = n * row_bytes;
-    L.idx0 = L.b0 + stages * L.b_stage_bytes;
-    uint32_t off = L.idx0 + 2 * IDX_BUF_BYTES;
+    L.idx0 = L.b0 + substages * L.b_stage_bytes;
+    L.epi0 = L.idx0 + 2 * IDX_BUF_BYTES;
+    uint32_t off = L.epi0 + EPI_BYTES;
     L.full0 = off;
     L.empty0 = off + 8 * MAX_STAGES;
     L.tfull0 = off + 16 * MAX_STAGES;
     L.tempty0 = L.tfull0 + 16;
     L.tmem_slot = L.tfull0 + 64;
+    L.segtab = L.tfull0 + 96;
     return L;
 }
-static inline size_t smem_bytes(int n, int stages, int row_bytes) {
-    return 1024 + (size_t)stages * ((size_t)BM * row_bytes + (size_t)n * row_bytes) + 2 * IDX_BUF_BYTES + 16 * MAX_STAGES + 128;
+static inline size_t smem_bytes(int n, int substages, int row_bytes) {
+    return 1024 + (size_t)substages * ((size_t)BM * row_bytes + (size_t)n * row_bytes) + 2 * IDX_BUF_BYTES + EPI_BYTES +
+           16 * MAX_STAGES + 96 + SEGTAB_BYTES + 32;
 }
 
 __device__ __forceinline__ uint32_t seg_mask(const tl_conv_seg& sg, int64_t tile) {
@@ -265,12 +322,15 @@ __device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
     return v;
 }
 
-// Warp roles (704 threads, one CTA per SM, persistent over work items = (row tile, K split)):
-//   warps  0..15  producers: G groups of 4 warps; group g fills the chunks whose ordinal in the CTA's stream is g mod G
-//   warps 16..19  epilogue (TMEM lane quarter = warp % 4)
+// Warp roles (736 threads, one CTA per SM, persistent over work items = (row tile, K split)):
+//   warps  0..15  producers: G groups of 4 warps; group g gathers the A rows of the chunks whose ordinal in the CTA's
+//                 stream is g mod G (4 cp.async of 16 B per thread and chunk; completion via mbarrier noinc arrive)
+//   warps 16..19  epilogue (TMEM lane quarter = warp % 4); rows are transposed through a per-warp shared-memory tile so
+//                 that every global load/store instruction covers whole 128 B lines
 //   warp  20      MMA issuer (lane 0) + TMEM alloc/dealloc
 //   warp  21      scheduler: one work item ahead it stages the item's rulebook rows (cp.async) and the list of live
 //                 (segment, offset, k-block) chunks in shared memory, so nobody else evaluates masks or split ranges
+//   warp  22      weight loader (lane 0): one TMA bulk copy per chunk of the pre-swizzled [C_out x 32] weight slab
 template <int EB>   // bytes per operand element: 4 = fp32 storage / kind::tf32, 2 = fp16 storage / kind::f16
 __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const tl_conv_desc d, const Launch P) {
     constexpr int ROW = BK * EB;          // bytes per operand row in a stage (one swizzle row)
@@ -281,7 +341,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const tl_conv_desc d, c
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int N = d.c_out;
-    const Layout L = carve(base, N, P.stages, ROW);
+    const Layout L = carve(base, N, P.stages * P.q, ROW);
+    const uint32_t Q = (uint32_t)P.q;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (L.tmem_slot - smem_u32(smem_raw)));
     const uint32_t S = (uint32_t)P.stages;
@@ -290,16 +351,24 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const tl_conv_desc d, c
 
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < S; ++s) {
-            mbar_init(L.full(s), kProducerThreads);
+            mbar_init(L.full(s), kProducerThreads + 1);   // 128 gather threads + the weight loader's expect_tx arrive
             mbar_init(L.empty(s), 1);
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(L.tfull(b), 1);
             mbar_init(L.tempty(b), kEpilogueThreads);
             mbar_init(L.wfull(b), 33);                               // 32 cp.async completions + lane 0
-            mbar_init(L.wempty(b), 128 * P.groups + kEpilogueThreads + 1);   // every reader of the descriptor
+            mbar_init(L.wempty(b), 128 * P.groups + kEpilogueThreads + 2);   // every reader of the descriptor
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x < d.n_seg) {   // per-segment constants the producers / weight loader look up by segment id
+        const tl_conv_seg& sg = d.seg[threadIdx.x];
+        const uint32_t t = L.segtab + 32 * threadIdx.x;
+        const uint64_t src = (uint64_t)sg.src, wgt = (uint64_t)sg.weight;
+        st_shared_v4(t, (uint32_t)src, (uint32_t)(src >> 32), (uint32_t)wgt, (uint32_t)(wgt >> 32));
+        st_shared_v4(t + 16, (uint32_t)(sg.src_stride * EB), (uint32_t)(sg.c_in / BK),
+                     sg.index ? (uint32_t)P.idx_base[threadIdx.x] : 0xffffffffu, 0u);
     }
     if (warp == kMmaWarp) {  // TMEM allocation is owned by the MMA warp
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(L.tmem_slot),
@@ -356,29 +425,24 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const tl_conv_desc d, c
             if (lane == 0) mbar_arrive(L.wfull(buf));
         }
     } else if (warp < 4 * P.groups) {
-        // ===================== producers: gather A rows + copy B slab ==============================
+        // ===================== producers: gather A rows =============================================
         // A thread never waits for its copies: `cp.async.mbarrier.arrive.noinc` makes the stage's full barrier count
         // this thread once all its prior cp.async have landed (the CUTLASS sm100 cp.async->UMMA hand-off), so up to S
         // chunks are in flight per CTA.
         const int group = warp >> 2, gw = warp & 3;       // producer group, warp within group
-        const int ptid = threadIdx.x & 127;               // thread within group
         const int chunk = lane % CH, sub = lane / CH;
-        const int col = gw * 32 + lane;                   // tile row whose rulebook entry this thread reads
         // 16 B chunk c of row r lives at chunk c ^ (r & 7) (128 B rows, SWIZZLE_128B) or c ^ ((r >> 1) & 3) (64 B, SWIZZLE_64B)
         auto swz = [](int c, int r) { return ROW == 128 ? (c ^ (r & 7)) : (c ^ ((r >> 1) & 3)); };
-        uint32_t a_off[NI];
+        uint32_t a_off[NI];                               // stage offset of my 16 B chunk in row gw*32 + i*RPI + sub
 #pragma unroll
         for (int i = 0; i < NI; ++i) {
             const int rl = i * RPI + sub;
             a_off[i] = (uint32_t)((gw * 32 + rl) * ROW + (swz(chunk, rl) << 4));
         }
-        constexpr int BROWS = 128 / CH;                   // B rows copied per pass of the group's 128 threads
-        const int brow = ptid / CH;                       // B rows brow + BROWS j
-        const uint32_t b_off0 = (uint32_t)(brow * ROW + (swz(chunk, brow) << 4));
-        const int nb = N / BROWS;
+        const int my_col = gw * 32 + sub;                 // tile row of slot i is my_col + i * RPI
         const uint32_t G = (uint32_t)P.groups;
-        uint32_t my_next = (uint32_t)group;    // ordinal (in this CTA's chunk stream) of my group's next chunk
-        uint32_t c0 = 0;                       // ordinal of the current work item's first chunk
+        uint32_t my_next = (uint32_t)group;    // ordinal (in this CTA's stream of Q-chunk slots) of my group's next slot fill
+        uint32_t c0 = 0;                       // ordinal of the current work item's first slot fill
         uint32_t slot = (uint32_t)group, phase = 0;   // ring position of my_next (G <= S)
         uint32_t witer = 0;
         for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++witer) {
@@ -387,58 +451,111 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const tl_conv_desc d, c
             const uint32_t buf = witer & 1u;
             mbar_wait(L.wfull(buf), (witer >> 1) & 1u);
             const uint32_t n = ld_shared_u32(L.count(buf));
-            uint32_t prev_sk = 0xffffffffu;
-            const char* rp[NI];
+            const uint32_t nfill = (n + Q - 1) / Q;
+            uint32_t prev_sk = 0xffffffffu, prev_s = 0xffffffffu;
+            uint64_t seg_src = 0;
+            uint32_t seg_stride = 0, seg_idx = 0xffffffffu;
+            uint64_t rp[NI];
             uint32_t vmask = 0;
-            const char* wk = nullptr;
-            int64_t wrow_stride = 0;
-            while (my_next < c0 + n) {
-                const uint32_t e = ld_shared_u32(L.list(buf, (int)(my_next - c0)));
-                const int kb = (int)(e & 7u);
-                if ((e >> 3) != prev_sk) {     // new (segment, offset): row pointers of my 8 (row, 16 B chunk) slots
-                    prev_sk = e >> 3;
-                    const int s = (int)(e >> 8), k = (int)((e >> 3) & 31u);
-                    const tl_conv_seg& sg = d.seg[s];
-                    int my_row;
-                    if (sg.index) my_row = ld_shared_i32(L.idx(buf, P.idx_base[s] + k, col));
-                    else my_row = (row0 + col) < d.n_out ? (int)(row0 + col) : -1;
-                    vmask = 0;
-#pragma unroll
-                    for (int i = 0; i < NI; ++i) {
-                        const int r = __shfl_sync(0xffffffffu, my_row, i * RPI + sub);
-                        vmask |= (r >= 0 ? 1u : 0u) << i;
-                        rp[i] = reinterpret_cast<const char*>(sg.src) + (int64_t)max(r, 0) * sg.src_stride * EB + chunk * 16;
-                    }
-                    wk = reinterpret_cast<const char*>(sg.weight) + ((int64_t)k * N + brow) * sg.c_in * EB + chunk * 16;
-                    wrow_stride = (int64_t)BROWS * sg.c_in * EB;
-                }
+            while (my_next < c0 + nfill) {
+                const uint32_t j0 = (my_next - c0) * Q;
+                const uint32_t cnt = min(Q, n - j0);
                 mbar_wait(L.empty(slot), phase ^ 1u);
-                const uint32_t a_st = L.a(slot), b_st = L.b(slot) + b_off0;
-                if (P.debug & 2) {
-                } else if (P.use_cg) {
+                for (uint32_t qi = 0; qi < cnt; ++qi) {
+                    const uint32_t e = ld_shared_u32(L.list(buf, (int)(j0 + qi)));
+                    const uint32_t kb = e & 7u;
+                    if ((e >> 3) != prev_sk) {     // new (segment, offset): source addresses of my NI (row, 16 B chunk) slots
+                        prev_sk = e >> 3;
+                        const uint32_t s = e >> 8, k = (e >> 3) & 31u;
+                        if (s != prev_s) {
+                            prev_s = s;
+                            const uint2 sa = ld_shared_u2(L.segtab + 32 * s);
+                            const uint2 sb = ld_shared_u2(L.segtab + 32 * s + 16);
+                            seg_src = ((uint64_t)sa.y << 32 | sa.x) + (uint32_t)(chunk * 16);
+                            seg_stride = sb.x;
+                            seg_idx = ld_shared_u32(L.segtab + 32 * s + 24);
+                        }
+                        vmask = 0;
 #pragma unroll
-                    for (int i = 0; i < NI; ++i)
-                        cp_async16_cg(a_st + a_off[i], rp[i] + kb * ROW, ((vmask >> i) & 1u) ? 16u : 0u);
-                } else {
+                        for (int i = 0; i < NI; ++i) {
+                            int r;
+                            if (seg_idx != 0xffffffffu) r = ld_shared_i32(L.idx(buf, (int)(seg_idx + k), my_col + i * RPI));
+                            else r = (row0 + my_col + i * RPI) < d.n_out ? (int)(row0 + my_col + i * RPI) : -1;
+                            vmask |= (r >= 0 ? 1u : 0u) << i;
+                            rp[i] = seg_src + (uint64_t)(uint32_t)max(r, 0) * seg_stride;   // absent: zero-filled copy (src-size 0)
+                        }
+                    }
+                    const uint32_t a_st = L.a(slot * Q + qi);
+                    const uint32_t koff = kb * ROW;
+                    if (P.debug & 2) {
+                    } else if (P.use_cg) {
 #pragma unroll
-                    for (int i = 0; i < NI; ++i)
-                        cp_async16(a_st + a_off[i], rp[i] + kb * ROW, ((vmask >> i) & 1u) ? 16u : 0u);
-                }
-                if (!(P.debug & 8)) {
-                    const char* wp = wk + kb * ROW;
-                    for (int j = 0; j < nb; ++j) cp_async16(b_st + j * (BROWS * ROW), wp + j * wrow_stride, 16u);
+                        for (int i = 0; i < NI; ++i)
+                            cp_async16_cg(a_st + a_off[i], reinterpret_cast<const void*>(rp[i] + koff),
+                                          ((vmask >> i) & 1u) ? 16u : 0u);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < NI; ++i)
+                            cp_async16(a_st + a_off[i], reinterpret_cast<const void*>(rp[i] + koff),
+                                       ((vmask >> i) & 1u) ? 16u : 0u);
+                    }
                 }
                 cp_async_mbar_arrive_noinc(L.full(slot));
                 my_next += G;
                 slot += G;
                 if (slot >= S) slot -= S, phase ^= 1u;
             }
-            c0 += n;
+            c0 += nfill;
             mbar_arrive(L.wempty(buf));
         }
+    } else if (warp == kWeightWarp) {
+        // ===================== weight loader: one TMA bulk copy per chunk ==========================
+        // weights are packed [n_off][c_in/32][C_out][32] with the 16 B chunks of every row already swizzled, so the
+        // slab of a chunk is one contiguous C_out x ROW block that lands in the B stage as-is
+        {
+            const uint32_t slab = (uint32_t)N * ROW;
+            uint64_t wbase[TL_MAX_SEG];
+            uint32_t wkb[TL_MAX_SEG];
+#pragma unroll
+            for (int s = 0; s < TL_MAX_SEG; ++s) {
+                wbase[s] = s < d.n_seg ? (uint64_t)d.seg[s].weight : 0;
+                wkb[s] = s < d.n_seg ? (uint32_t)(d.seg[s].c_in / BK) : 1u;
+            }
+            uint32_t slot = 0, phase = 0, witer = 0;
+            for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++witer) {
+                const uint32_t buf = witer & 1u;
+                mbar_wait(L.wfull(buf), (witer >> 1) & 1u);
+                const uint32_t n = ld_shared_u32(L.count(buf));
+                for (uint32_t j0 = 0; j0 < n; j0 += Q) {
+                    const uint32_t cnt = min(Q, n - j0);
+                    mbar_wait(L.empty(slot), phase ^ 1u);
+                    if (elect_one()) {
+                        if (P.debug & 8) {
+                            mbar_arrive(L.full(slot));
+                        } else {
+                            mbar_arrive_expect_tx(L.full(slot), cnt * slab);
+                            for (uint32_t qi = 0; qi < cnt; ++qi) {
+                                const uint32_t e = ld_shared_u32(L.list(buf, (int)(j0 + qi)));
+                                const uint32_t s = e >> 8, k = (e >> 3) & 31u, kb = e & 7u;
+                                const uint64_t wb = s == 0 ? wbase[0] : (s == 1 ? wbase[1] : wbase[2]);
+                                const uint32_t kbs = s == 0 ? wkb[0] : (s == 1 ? wkb[1] : wkb[2]);
+                                bulk_g2s(L.b(slot * Q + qi), reinterpret_cast<const void*>(wb + (uint64_t)(k * kbs + kb) * slab),
+                                         slab, L.full(slot));
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (++slot == S) slot = 0, phase ^= 1u;
+                }
+                if (elect_one()) mbar_arrive(L.wempty(buf));
+                __syncwarp();
+            }
+        }
     } else if (warp >= kFirstEpilogueWarp && warp < kFirstEpilogueWarp + 4) {
-        // ===================== epilogue: TMEM -> registers -> global ================================
+        // ===================== epilogue: TMEM -> registers -> (smem transpose) -> global ============
         const int ew = warp - kFirstEpilogueWarp;  // == warp % 4: the TMEM lane quarter this warp may touch
+        const uint32_t epi = L.epi0 + (uint32_t)ew * (32 * 128);
+        const int cc = lane & 7, rsub = lane >> 3;  // after the transpose: lane holds 4 columns (cc) of row i*4 + rsub
         uint32_t titer = 0;
         for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++titer) {
             const int tile = w / P.splits;
@@ -448,32 +565,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const tl_conv_desc d, c
             mbar_arrive(L.wempty(buf));
             mbar_wait(L.tfull(buf), (titer >> 1) & 1u);
             tc_fence_after();
-            const int64_t row = (int64_t)tile * BM + ew * 32 + lane;
-            const bool live = row < d.n_out && !(P.debug & 4);
+            const int64_t wrow0 = (int64_t)tile * BM + ew * 32;   // first row of this warp's quarter
             const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + buf * P.buf_cols;
-            if (P.splits > 1) {
-                if (any) {
-                    for (int c0 = 0; c0 < N; c0 += 32) {
-                        uint32_t acc[32];
-                        tmem_ld32(taddr + c0, acc);
-                        for (int way = 1; way < P.acc_ways; ++way) {
-                            uint32_t more[32];
-                            tmem_ld32(taddr + way * P.acc_cols + c0, more);
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(__uint_as_float(acc[j]) + __uint_as_float(more[j]));
-                        }
-                        if (live) {
-                            float* wp = P.splitk_ws + row * N + c0;
-#pragma unroll
-                            for (int j = 0; j < 8; ++j)   // 16 B vector reductions: 4x fewer L2 atomic operations
-                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(wp + 4 * j),
-                                             "f"(__uint_as_float(acc[4 * j])), "f"(__uint_as_float(acc[4 * j + 1])),
-                                             "f"(__uint_as_float(acc[4 * j + 2])), "f"(__uint_as_float(acc[4 * j + 3]))
-                                             : "memory");
-                        }
-                    }
-                }
-            } else {
+            if (any || P.splits == 1) {
                 for (int c0 = 0; c0 < N; c0 += 32) {
                     uint32_t acc[32];
                     if (any) {
@@ -484,31 +578,50 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const tl_conv_desc d, c
 #pragma unroll
                             for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(__uint_as_float(acc[j]) + __uint_as_float(more[j]));
                         }
-                    } else
+                    } else {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) acc[j] = 0u;
-                    if (live) {
-                        const int64_t o = row * N + c0;
-                        float v[32];
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-                        if (d.residual) {
-                            const float4* rp = reinterpret_cast<const float4*>(d.residual + o);
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const float4 r4 = __ldg(rp + j);
-                                v[4 * j] += r4.x, v[4 * j + 1] += r4.y, v[4 * j + 2] += r4.z, v[4 * j + 3] += r4.w;
-                            }
-                        }
-                        if (d.out_raw) {
-                            float4* op = reinterpret_cast<float4*>(d.out_raw + o);
-#pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                        }
-                        if (d.out_act1) store_act32<EB>(d.out_act1, o, v, d.scale1 + c0, d.shift1 + c0);
-                        if (d.out_act2) store_act32<EB>(d.out_act2, o, v, d.scale2 + c0, d.shift2 + c0);
                     }
+                    // row `lane` -> shared (16 B chunk j at j ^ (lane & 7): conflict-free both ways)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        st_shared_v4(epi + lane * 128 + ((j ^ (lane & 7)) << 4), acc[4 * j], acc[4 * j + 1], acc[4 * j + 2],
+                                     acc[4 * j + 3]);
+                    __syncwarp();
+                    const int col = c0 + 4 * cc;
+                    float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), t1 = s1, s2 = s1, t2 = s1;
+                    if (d.out_act1) s1 = __ldg(reinterpret_cast<const float4*>(d.scale1 + col)), t1 = __ldg(reinterpret_cast<const float4*>(d.shift1 + col));
+                    if (d.out_act2) s2 = __ldg(reinterpret_cast<const float4*>(d.scale2 + col)), t2 = __ldg(reinterpret_cast<const float4*>(d.shift2 + col));
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int r = i * 4 + rsub;
+                        float4 v = ld_shared_f4(epi + r * 128 + ((cc ^ (r & 7)) << 4));
+                        const int64_t grow = wrow0 + r;
+                        if (grow >= d.n_out || (P.debug & 4)) continue;
+                        const int64_t o = grow * N + col;
+                        if (P.splits > 1) {   // 16 B vector reductions into the split-K buffer
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(P.splitk_ws + o), "f"(v.x),
+                                         "f"(v.y), "f"(v.z), "f"(v.w)
+                                         : "memory");
+                            continue;
+                        }
+                        if (d.residual) {
+                            const float4 r4 = __ldg(reinterpret_cast<const float4*>(d.residual + o));
+                            v.x += r4.x, v.y += r4.y, v.z += r4.z, v.w += r4.w;
+                        }
+                        if (d.out_raw) *reinterpret_cast<float4*>(d.out_raw + o) = v;
+                        if (d.out_act1) {
+                            const float a0 = fmaxf(fmaf(v.x, s1.x, t1.x), 0.f), a1 = fmaxf(fmaf(v.y, s1.y, t1.y), 0.f);
+                            const float a2 = fmaxf(fmaf(v.z, s1.z, t1.z), 0.f), a3 = fmaxf(fmaf(v.w, s1.w, t1.w), 0.f);
+                            store_act4<EB>(d.out_act1, o, a0, a1, a2, a3);
+                        }
+                        if (d.out_act2) {
+                            const float a0 = fmaxf(fmaf(v.x, s2.x, t2.x), 0.f), a1 = fmaxf(fmaf(v.y, s2.y, t2.y), 0.f);
+                            const float a2 = fmaxf(fmaf(v.z, s2.z, t2.z), 0.f), a3 = fmaxf(fmaf(v.w, s2.w, t2.w), 0.f);
+                            store_act4<EB>(d.out_act2, o, a0, a1, a2, a3);
+                        }
+                    }
+                    __syncwarp();
                 }
             }
             tc_fence_before();
@@ -516,7 +629,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const tl_conv_desc d, c
         }
     } else if (warp == kMmaWarp) {
         // ===================== MMA issuer (one elected thread) ======================================
-        if (lane == 0) {
+        {
             const uint32_t idesc = make_idesc(N, EB == 2);
             const uint64_t adesc0 = make_smem_desc(L.a0, ROW), bdesc0 = make_smem_desc(L.b0, ROW);
             const uint32_t a_step = L.a_stage_bytes >> 4, b_step = L.b_stage_bytes >> 4;
@@ -526,36 +639,46 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const tl_conv_desc d, c
                 const uint32_t buf = titer & 1u;
                 mbar_wait(L.wfull(buf), (titer >> 1) & 1u);
                 const uint32_t n = ld_shared_u32(L.count(buf));
-                mbar_arrive(L.wempty(buf));
+                __syncwarp();
+                if (elect_one()) mbar_arrive(L.wempty(buf));
                 mbar_wait(L.tempty(buf), ((titer >> 1) & 1u) ^ 1u);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + buf * P.buf_cols;
-                for (uint32_t c = 0; c < n; ++c) {
+                for (uint32_t j0 = 0; j0 < n; j0 += Q) {
+                    const uint32_t cnt = min(Q, n - j0);
                     mbar_wait(L.full(slot), phase);
                     tc_fence_after();
-                    const uint64_t adesc = adesc0 + (uint64_t)(slot * a_step);
-                    const uint64_t bdesc = bdesc0 + (uint64_t)(slot * b_step);
-                    if (!(P.debug & 1)) {
+                    if (elect_one()) {
+                        if (!(P.debug & 1)) {
+                            uint64_t adesc = adesc0 + (uint64_t)(slot * Q * a_step);
+                            uint64_t bdesc = bdesc0 + (uint64_t)(slot * Q * b_step);
+                            for (uint32_t qi = 0; qi < cnt; ++qi, adesc += a_step, bdesc += b_step) {
 #pragma unroll
-                        for (int kk = 0; kk < KSTEPS; ++kk) {  // UMMA K step = 32 B (8 tf32 / 16 fp16): advance inside the swizzle atom
-                            // K-step kk accumulates into its own TMEM tile kk % ways (the epilogue adds the tiles up)
-                            const uint32_t way = (uint32_t)kk & wmask;
-                            if (EB == 4)
-                                umma_tf32(tmem_d + way * P.acc_cols, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2),
-                                          idesc, (c == 0 && (uint32_t)kk <= wmask) ? 0u : 1u);
-                            else
-                                umma_f16(tmem_d + way * P.acc_cols, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2),
-                                         idesc, (c == 0 && (uint32_t)kk <= wmask) ? 0u : 1u);
+                                for (int kk = 0; kk < KSTEPS; ++kk) {  // UMMA K step = 32 B (8 tf32 / 16 fp16): advance inside the swizzle atom
+                                    // K-step kk accumulates into its own TMEM tile kk % ways (the epilogue adds the tiles up)
+                                    const uint32_t way = (uint32_t)kk & wmask;
+                                    const uint32_t accum = (j0 + qi == 0 && (uint32_t)kk <= wmask) ? 0u : 1u;
+                                    if (EB == 4)
+                                        umma_tf32(tmem_d + way * P.acc_cols, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2),
+                                                  idesc, accum);
+                                    else
+                                        umma_f16(tmem_d + way * P.acc_cols, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2),
+                                                 idesc, accum);
+                                }
+                            }
                         }
+                        umma_commit(L.empty(slot));
                     }
-                    umma_commit(L.empty(slot));
+                    __syncwarp();
                     if (++slot == S) slot = 0, phase ^= 1u;
                 }
-                if (n == 0) mbar_arrive(L.tfull(buf));  // no pair in this work item: nothing to accumulate
-                else umma_commit(L.tfull(buf));
+                if (elect_one()) {
+                    if (n == 0) mbar_arrive(L.tfull(buf));  // no pair in this work item: nothing to accumulate
+                    else umma_commit(L.tfull(buf));
+                }
+                __syncwarp();
             }
         }
-        __syncwarp();
     }
 
     tc_fence_before();
@@ -670,7 +793,7 @@ int conv_fwd_tc(const tl_conv_desc& d, cudaStream_t stream, bool half) {
         TL_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
         TL_CUDA_CHECK(cudaFuncSetAttribute(tc::k_conv_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         TL_CUDA_CHECK(cudaFuncSetAttribute(tc::k_conv_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        smem_budget = env_int("TL_TC_SMEM_KB", 200) * 1024;   // keep the rest of the 228 KB as L1 for the gather
+        smem_budget = env_int("TL_TC_SMEM_KB", 212) * 1024;   // keep the rest of the 228 KB as L1 for the gather
         split_target = env_int("TL_TC_SPLIT_WAVES", 1);        // split-K until work items >= waves * SMs
     }
     const int n = d.c_out;
@@ -682,21 +805,24 @@ int conv_fwd_tc(const tl_conv_desc& d, cudaStream_t stream, bool half) {
     while (P.acc_ways > 1 && (2 * P.acc_ways * P.acc_cols > 512 || P.acc_ways > row_bytes / 32)) P.acc_ways >>= 1;
     P.buf_cols = P.acc_ways * P.acc_cols;
     P.tmem_cols = 2 * P.buf_cols;  // <= 512
-    const size_t stage = (size_t)(tc::BM + n) * row_bytes;
-    int stages = (int)((smem_budget - 2048 - 2 * tc::IDX_BUF_BYTES) / stage);
-    if (stages < 4) stages = 4;
+    // ring = `stages` slots of `q` chunks each (a chunk = 128 gathered rows + the [C_out x 32] weight slab); one barrier
+    // round trip hands over a whole slot, so the single-warp MMA / weight-loader loops pay their fixed cost once per q chunks
+    const size_t sub = (size_t)(tc::BM + n) * row_bytes;
+    const int ring_budget = smem_budget - 2048 - 2 * tc::IDX_BUF_BYTES - tc::EPI_BYTES;
+    int q = env_int("TL_TC_Q", 4);
+    while (q > 1 && (size_t)ring_budget / (q * sub) < 3) q >>= 1;
+    int stages = (int)(ring_budget / (q * sub));
+    if (stages < 2) stages = 2;
     if (stages > tc::MAX_STAGES) stages = tc::MAX_STAGES;
-    while (tc::smem_bytes(n, stages, row_bytes) > 227 * 1024 && stages > 2) --stages;
+    while (tc::smem_bytes(n, stages * q, row_bytes) > 227 * 1024 && stages > 2) --stages;
     P.stages = stages;
-    // two producer groups alternate chunks, each keeps `lag` of its own cp.async groups in flight before publishing
-    // the oldest; 2*lag < stages keeps the ring deadlock-free (a group can always publish what the MMA waits for)
+    P.q = q;
+    // the producer groups take the CTA's slot fills round-robin; G <= stages keeps the ring deadlock-free
     int groups = env_int("TL_TC_GROUPS", tc::kMaxGroups);
     while (groups > 1 && (groups > stages || groups > tc::kMaxGroups)) groups >>= 1;
     P.groups = groups;
-    P.lag = (stages - 1) / groups;     // G * lag < stages: the ring cannot deadlock
-    if (P.lag < 1) P.lag = 1;
     P.use_cg = env_int("TL_TC_CG", 1);
-    const size_t smem = tc::smem_bytes(n, stages, row_bytes);
+    const size_t smem = tc::smem_bytes(n, stages * q, row_bytes);
     P.num_tiles = (d.n_out + tc::BM - 1) / tc::BM;
     P.chunks_total = 0;
     for (int s = 0; s < d.n_seg; ++s) P.chunks_total += d.seg[s].n_off * (d.seg[s].c_in / tc::BK);

@@ -66,3 +66,56 @@ def segment_plot(model, tiles, grouping_cfg, group=None):
     labels, n_clusters = pipeline.instances_cuda(coords, vals[:, 2:5].contiguous(), vals[:, 0:2].contiguous(),
                                                  vals[:, 5].contiguous(), grouping_cfg)
     return coords, labels, n_clusters
+
+
+# ---- data-parallel training (BASELINE.json config 5) -----------------------------------------------
+def grad_buckets(model):
+    """Parameters grouped for the gradient all-reduce: one bucket per U-Net level (depth = number of '.u.' hops in
+    the reference's module path, tree_learn/model/blocks.py:97-135) plus one for the input conv / output layer /
+    heads.  Ordered deepest level first -- the order in which backward finishes their weight gradients last-to-first
+    is irrelevant for correctness; the split keeps every NCCL call in the tens-of-MB range (level 6 alone holds
+    ~11 M of the 30 M parameters)."""
+    buckets = {}
+    for name, p in model.named_parameters():
+        if not p.requires_grad:
+            continue
+        depth = name.split('.').count('u') if name.startswith('unet.') else -1
+        buckets.setdefault(depth, []).append(p)
+    return [buckets[d] for d in sorted(buckets, reverse=True)]
+
+
+def allreduce_grads(model, group=None):
+    """Average `.grad` over ranks (identical replicas, per-GPU BatchNorm statistics -- the reference has no SyncBN):
+    one flat all-reduce(sum) per bucket, launched asynchronously and waited together, then scaled by 1/world."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return
+    world = dist.get_world_size(group)
+    if world == 1:
+        return
+    pending = []
+    for params in grad_buckets(model):
+        grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in params]
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        pending.append((dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=True), flat, params))
+    for work, flat, params in pending:
+        work.wait()
+        flat.mul_(1.0 / world)
+        off = 0
+        for p in params:
+            n = p.numel()
+            p.grad = flat[off:off + n].view_as(p).clone() if p.grad is None else p.grad.copy_(flat[off:off + n].view_as(p))
+            off += n
+
+
+def train_step(model, optimizer, batch, group=None, grad_clip=None):
+    """One data-parallel training step on this rank's batch (tools/training/train.py:32-44 without AMP):
+    forward + loss, backward, gradient all-reduce, optional clip, optimizer step.  Returns (loss, loss_dict)."""
+    model.train()
+    optimizer.zero_grad(set_to_none=True)
+    loss, loss_dict = model(batch, return_loss=True)
+    loss.backward()
+    allreduce_grads(model, group)
+    if grad_clip:
+        torch.nn.utils.clip_grad_norm_([p for p in model.parameters() if p.requires_grad], grad_clip)
+    optimizer.step()
+    return loss.detach(), {k: v.detach() for k, v in loss_dict.items()}

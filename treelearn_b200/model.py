@@ -169,9 +169,9 @@ class TreeLearn(nn.Module):
                     out = []
                     for piece in pieces:
                         if half and tc_eligible(piece.shape[2], co) and 'i_branch' not in name:
-                            out.append(piece.permute(1, 0, 2).contiguous().half())          # fp16 [K, Co, Ci]
+                            out.append(sparse.pack_weight_tc(piece.permute(1, 0, 2), True))    # fp16 B-operand slabs
                         elif tf32 and tc_eligible(piece.shape[2], co):
-                            out.append(_round_tf32(piece.permute(1, 0, 2).contiguous()))   # [K, Co, Ci] K-major B operand
+                            out.append(sparse.pack_weight_tc(piece.permute(1, 0, 2), False))   # TF32 B-operand slabs
                         else:
                             out.append(piece.permute(1, 2, 0).contiguous())               # [K, Ci, Co] SIMT layout
                     pk[name] = out

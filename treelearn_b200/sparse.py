@@ -131,6 +131,29 @@ class Seg:
     mask: Optional[torch.Tensor] = None
 
 
+def round_tf32(w):
+    """Round-to-nearest-even to TF32 (10 explicit mantissa bits) so the tensor core's operand truncation is exact."""
+    i = w.contiguous().view(torch.int32)
+    return ((i + 0x0FFF + ((i >> 13) & 1)) & ~0x1FFF).view(torch.float32)
+
+
+def pack_weight_tc(w, half):
+    """w [n_off, C_out, C_in] -> the tcgen05 path's B-operand layout [n_off, C_in/32, C_out, 32]: one contiguous
+    [C_out x 32-channel] slab per (offset, k-block) whose rows already carry the UMMA shared-memory swizzle (16 B chunk
+    c of row n sits at c ^ (n & 7) for 128 B fp32/TF32 rows, at c ^ ((n >> 1) & 3) for 64 B fp16 rows), so the kernel
+    lands a slab in its B stage with a single TMA bulk copy.  fp16 when `half`, else fp32 rounded to TF32."""
+    k, co, ci = w.shape
+    assert ci % 32 == 0 and co % 32 == 0, (ci, co)
+    t = w.detach().half() if half else round_tf32(w.detach().float())
+    ch = 4 if half else 8                      # 16 B chunks per 32-channel row
+    t = t.reshape(k, co, ci // 32, ch, 32 // ch).permute(0, 2, 1, 3, 4)      # [k, kb, co, chunk, elems]
+    n = torch.arange(co, device=w.device)
+    x = ((n >> 1) & 3) if half else (n & 7)
+    src_chunk = torch.arange(ch, device=w.device)[None, :] ^ x[:, None]     # destination chunk c holds source chunk c ^ x
+    t = torch.gather(t, 3, src_chunk[None, None, :, :, None].expand(k, ci // 32, co, ch, 32 // ch))
+    return t.reshape(k, ci // 32, co, 32).contiguous()
+
+
 SPLITK_MAX_ROWS = 2 * 148 * TILE_ROWS   # below two waves of 128-row tiles the library may split K over CTAs
 PROFILE = None   # bench.py sets this to a list: every conv launch appends (start_evt, end_evt, alg_bytes, flops)
 
