@@ -52,7 +52,7 @@ def identity_geom(n):
 
 
 def _tc_ok(c_in, c_out):
-    return c_in % 32 == 0 and c_out % 32 == 0 and c_out <= 256
+    return c_in % 32 == 0 and c_in <= 256 and c_out % 32 == 0 and c_out <= 256
 
 
 def _round_tf32(w):

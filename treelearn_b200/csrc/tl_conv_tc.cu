@@ -29,20 +29,22 @@ namespace tc {
 constexpr int BM = 128;          // rows per tile == TMEM lanes
 constexpr int BK = 32;           // channels per K block: one swizzle row of 128 B (fp32/TF32 operands) or 64 B (fp16)
 constexpr int MAX_STAGES = 12;
-constexpr int kMaxGroups = 4;            // producer groups of four warps; group g fills the chunks with ordinal % G == g
-constexpr int kProducerWarps = 4 * kMaxGroups;
-constexpr int kProducerThreads = 128;    // cp.async arrivals per stage (one group); +1 arrival from the weight loader
+constexpr int kProducerWarps = 12;       // gather warps: groups of q warps, group g fills the ring slots with ordinal % G == g
 constexpr int kEpilogueThreads = 128;
-constexpr int kFirstEpilogueWarp = kProducerWarps;      // 16..19: warp % 4 == TMEM lane quarter
-constexpr int kMmaWarp = kProducerWarps + 4;            // 20
-constexpr int kSchedWarp = kProducerWarps + 5;          // 21: builds each work item's descriptor (rulebook rows + chunk list)
-constexpr int kWeightWarp = kProducerWarps + 6;         // 22: one thread bulk-copies (TMA) each chunk's weight slab
+constexpr int kFirstEpilogueWarp = kProducerWarps;      // 12..15: warp % 4 == TMEM lane quarter
+constexpr int kMmaWarp = kProducerWarps + 4;            // 16
+constexpr int kSchedWarp = kProducerWarps + 5;          // 17: builds each work item's descriptor (rulebook rows + chunk list)
+constexpr int kWeightWarp = kProducerWarps + 6;         // 18: one thread bulk-copies (TMA) each chunk's weight slab
 constexpr int kThreads = 32 * (kProducerWarps + 4 + 3);
 constexpr int MAX_CHUNKS = 448;                         // live (segment, offset, k-block) entries per work item
 constexpr int IDX_ROWS = 32;                         // rulebook rows (segment, offset) staged per tile
 constexpr int IDX_BUF_BYTES = IDX_ROWS * BM * 4 + MAX_CHUNKS * 4 + 64;   // rulebook rows + chunk list + count; x2
 constexpr int EPI_BYTES = 4 * 32 * 128;              // per epilogue warp: 32 rows x 32 fp32 columns, transposed for coalescing
 constexpr int SEGTAB_BYTES = 32 * TL_MAX_SEG;
+
+// 256 zero regions of 1 KB: source of absent neighbour rows in "zero row" gather mode (never written).  Spread out so the
+// reads do not serialise on one L2 line (a single shared zero row made the kernel 8x slower).
+__device__ float g_zero_rows[256 * 256];
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -64,6 +66,24 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "}\n" ::"r"(bar),
         "r"(parity)
         : "memory");
+}
+// per-tile waits (descriptor / accumulator hand-offs) back off between polls so that they do not steal issue slots
+// from the gather warps (measured: 20 % of all issued instructions were try_wait spins)
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (true) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) break;
+        __nanosleep(64);
+    }
 }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
@@ -259,6 +279,8 @@ struct Launch {   // per-launch scalars (kernel parameter)
     float* splitk_ws;  // [n_out, c_out] zeroed fp32 accumulation buffer when splits > 1
     int groups;        // active producer groups (power of two <= kMaxGroups, < stages)
     int use_cg;        // gather A rows with cp.async.cg (bypass L1) instead of .ca
+    int prefetch;      // 1: the scheduler bulk-prefetches (L2) the tile's own source rows of submanifold / identity segments
+    int zero_row;      // 1: absent neighbours read a zero row (every copy a uniform 16 B); 0: cp.async zero-fill (src-size 0)
     int idx_base[TL_MAX_SEG];   // first prefetch row of each indexed segment (segments sharing a table share rows); -1 = identity
     int idx_owner[TL_MAX_SEG];  // 1 = this segment's table rows are fetched (0 = alias of an earlier segment)
 };
@@ -322,21 +344,47 @@ __device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
     return v;
 }
 
-// Warp roles (736 threads, one CTA per SM, persistent over work items = (row tile, K split)):
-//   warps  0..15  producers: G groups of 4 warps; group g gathers the A rows of the chunks whose ordinal in the CTA's
+// One warp gathers the 128 rows of a chunk: lane (sub, chunk) copies the 16 B piece `chunk` of rows sub, sub + RPI, ...
+// Rulebook entries come from the staged table in batches of 8 (independent shared-memory loads first, copies after).
+// MODE 0: cp.async.cg with zero-fill for absent rows, 1: cp.async.ca with zero-fill, 2: cp.async.cg, absent rows read zeros.
+template <int EB, int MODE>
+__device__ __forceinline__ void gather_rows(uint32_t ia, uint32_t dst0, uint32_t a_off_even, uint32_t a_off_odd, uint64_t src0,
+                                            uint32_t seg_stride, uint64_t zsrc0, uint32_t zr0) {
+    constexpr int ROW = BK * EB, RPI = 32 / (ROW / 16), NR = BM / RPI, BATCH = 8;
+#pragma unroll
+    for (int i0 = 0; i0 < NR; i0 += BATCH) {
+        int r[BATCH];
+#pragma unroll
+        for (int b = 0; b < BATCH; ++b) r[b] = ld_shared_i32(ia + (uint32_t)((i0 + b) * RPI * 4));
+#pragma unroll
+        for (int b = 0; b < BATCH; ++b) {
+            const int i = i0 + b;
+            const uint32_t dst = dst0 + (uint32_t)(i * RPI * ROW) + ((i & 1) ? a_off_odd : a_off_even);
+            const uint64_t src = src0 + (uint64_t)(uint32_t)max(r[b], 0) * seg_stride;
+            if (MODE == 2)
+                cp_async16_cg(dst, reinterpret_cast<const void*>(r[b] >= 0 ? src : zsrc0 + (((zr0 + i) & 255u) << 10)), 16u);
+            else if (MODE == 0)
+                cp_async16_cg(dst, reinterpret_cast<const void*>(src), r[b] >= 0 ? 16u : 0u);
+            else
+                cp_async16(dst, reinterpret_cast<const void*>(src), r[b] >= 0 ? 16u : 0u);
+        }
+    }
+}
+
+// Warp roles (608 threads, one CTA per SM, persistent over work items = (row tile, K split)):
+//   warps  0..11  producers: G groups of 4 warps; group g gathers the A rows of the chunks whose ordinal in the CTA's
 //                 stream is g mod G (4 cp.async of 16 B per thread and chunk; completion via mbarrier noinc arrive)
-//   warps 16..19  epilogue (TMEM lane quarter = warp % 4); rows are transposed through a per-warp shared-memory tile so
+//   warps 12..15  epilogue (TMEM lane quarter = warp % 4); rows are transposed through a per-warp shared-memory tile so
 //                 that every global load/store instruction covers whole 128 B lines
-//   warp  20      MMA issuer (lane 0) + TMEM alloc/dealloc
-//   warp  21      scheduler: one work item ahead it stages the item's rulebook rows (cp.async) and the list of live
+//   warp  16      MMA issuer (lane 0) + TMEM alloc/dealloc
+//   warp  17      scheduler: one work item ahead it stages the item's rulebook rows (cp.async) and the list of live
 //                 (segment, offset, k-block) chunks in shared memory, so nobody else evaluates masks or split ranges
-//   warp  22      weight loader (lane 0): one TMA bulk copy per chunk of the pre-swizzled [C_out x 32] weight slab
+//   warp  18      weight loader (lane 0): one TMA bulk copy per chunk of the pre-swizzled [C_out x 32] weight slab
 template <int EB>   // bytes per operand element: 4 = fp32 storage / kind::tf32, 2 = fp16 storage / kind::f16
 __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const tl_conv_desc d, const Launch P) {
     constexpr int ROW = BK * EB;          // bytes per operand row in a stage (one swizzle row)
     constexpr int CH = ROW / 16;          // 16 B chunks per row
     constexpr int RPI = 32 / CH;          // rows covered by one warp-wide LDGSTS
-    constexpr int NI = 32 / RPI;          // LDGSTS per thread per A tile
     constexpr int KSTEPS = ROW / 32;      // UMMA K steps (32 B each) per stage
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -351,14 +399,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const tl_conv_desc d, c
 
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < S; ++s) {
-            mbar_init(L.full(s), kProducerThreads + 1);   // 128 gather threads + the weight loader's expect_tx arrive
+            mbar_init(L.full(s), 32 * P.q + 1);   // the group's gather threads + the weight loader's expect_tx arrive
             mbar_init(L.empty(s), 1);
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(L.tfull(b), 1);
             mbar_init(L.tempty(b), kEpilogueThreads);
             mbar_init(L.wfull(b), 33);                               // 32 cp.async completions + lane 0
-            mbar_init(L.wempty(b), 128 * P.groups + kEpilogueThreads + 2);   // every reader of the descriptor
+            mbar_init(L.wempty(b), 32 * P.q * P.groups + kEpilogueThreads + 2);   // every reader of the descriptor
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -386,13 +434,23 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const tl_conv_desc d, c
         uint32_t witer = 0;
         for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++witer) {
             const uint32_t buf = witer & 1u;
-            if (witer >= 2) mbar_wait(L.wempty(buf), ((witer >> 1) - 1u) & 1u);   // readers of item witer-2 are done
+            if (witer >= 2) mbar_wait_sleep(L.wempty(buf), ((witer >> 1) - 1u) & 1u);   // readers of item witer-2 are done
             const int tile = w / P.splits, split = w - tile * P.splits;
             const int lo = split * per_split, hi = min(lo + per_split, P.chunks_total);
             int ord = 0, pos = 0;
             for (int s = 0; s < d.n_seg; ++s) {
                 const tl_conv_seg& sg = d.seg[s];
                 const int kblocks = sg.c_in / BK;
+                if (P.prefetch && lane == 0 && (!sg.index || sg.n_off == 27) && sg.src_stride == sg.c_in) {
+                    // rows [128 t, 128 t + 128) of the source are this tile's centre taps and most of its 3^3 neighbours
+                    // (Morton order): pull them into L2 one work item ahead so the row gathers mostly hit L2
+                    const int64_t r0 = (int64_t)tile * BM;
+                    const int64_t rows = min((int64_t)BM, (int64_t)d.n_out - r0);
+                    const char* pa = reinterpret_cast<const char*>(sg.src) + r0 * sg.src_stride * EB;
+                    if (rows > 0)
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pa), "r"((uint32_t)(rows * sg.c_in * EB))
+                                     : "memory");
+                }
                 if (sg.index && P.idx_owner[s]) {   // rulebook rows: lane stages 4 tile rows (16 B) per offset
                     const int32_t* ip = sg.index + (int64_t)tile * BM + 4 * lane;
                     for (int k = 0; k < sg.n_off; ++k)
@@ -424,80 +482,73 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const tl_conv_desc d, c
             cp_async_mbar_arrive_noinc(L.wfull(buf));
             if (lane == 0) mbar_arrive(L.wfull(buf));
         }
-    } else if (warp < 4 * P.groups) {
+    } else if (warp < P.q * P.groups) {
         // ===================== producers: gather A rows =============================================
-        // A thread never waits for its copies: `cp.async.mbarrier.arrive.noinc` makes the stage's full barrier count
-        // this thread once all its prior cp.async have landed (the CUTLASS sm100 cp.async->UMMA hand-off), so up to S
-        // chunks are in flight per CTA.
-        const int group = warp >> 2, gw = warp & 3;       // producer group, warp within group
+        // A group = q warps fills one ring slot (q chunks): warp gw gathers ALL 128 rows of chunk gw, so the per-chunk
+        // bookkeeping (list entry, segment constants, barrier wait / arrive) is paid once per 128 rows.
+        // A thread never waits for its copies: `cp.async.mbarrier.arrive.noinc` makes the slot's full barrier count
+        // this thread once all its prior cp.async have landed (the CUTLASS sm100 cp.async->UMMA hand-off).
+        constexpr int NR = BM / RPI;                      // LDGSTS per lane and chunk (16 fp16 / 32 tf32)
+        constexpr int BATCH = 8;                          // rulebook entries fetched from shared memory per batch
+        const uint32_t group = (uint32_t)warp / Q, gw = (uint32_t)warp % Q;
         const int chunk = lane % CH, sub = lane / CH;
-        // 16 B chunk c of row r lives at chunk c ^ (r & 7) (128 B rows, SWIZZLE_128B) or c ^ ((r >> 1) & 3) (64 B, SWIZZLE_64B)
-        auto swz = [](int c, int r) { return ROW == 128 ? (c ^ (r & 7)) : (c ^ ((r >> 1) & 3)); };
-        uint32_t a_off[NI];                               // stage offset of my 16 B chunk in row gw*32 + i*RPI + sub
-#pragma unroll
-        for (int i = 0; i < NI; ++i) {
-            const int rl = i * RPI + sub;
-            a_off[i] = (uint32_t)((gw * 32 + rl) * ROW + (swz(chunk, rl) << 4));
-        }
-        const int my_col = gw * 32 + sub;                 // tile row of slot i is my_col + i * RPI
+        // 16 B chunk c of row r lives at chunk c ^ (r & 7) (128 B rows, SWIZZLE_128B) or c ^ ((r >> 1) & 3) (64 B, SWIZZLE_64B);
+        // rows advance by RPI per copy: the swizzle term is constant (64 B rows, RPI = 8) or alternates (128 B rows, RPI = 4)
+        const uint32_t a_off_even = (uint32_t)(sub * ROW + ((ROW == 128 ? (chunk ^ sub) : (chunk ^ ((sub >> 1) & 3))) << 4));
+        const uint32_t a_off_odd = (uint32_t)(sub * ROW + ((ROW == 128 ? (chunk ^ (sub + 4)) : (chunk ^ ((sub >> 1) & 3))) << 4));
+        const uint64_t zero_src = (uint64_t)g_zero_rows + (uint32_t)(chunk * 16);
         const uint32_t G = (uint32_t)P.groups;
-        uint32_t my_next = (uint32_t)group;    // ordinal (in this CTA's stream of Q-chunk slots) of my group's next slot fill
+        uint32_t my_next = group;              // ordinal (in this CTA's stream of slot fills) of my group's next fill
         uint32_t c0 = 0;                       // ordinal of the current work item's first slot fill
-        uint32_t slot = (uint32_t)group, phase = 0;   // ring position of my_next (G <= S)
+        uint32_t slot = group, phase = 0;      // ring position of my_next (G <= S)
         uint32_t witer = 0;
+        uint32_t prev_s = 0xffffffffu;
+        uint64_t seg_src = 0;
+        uint32_t seg_stride = 0, seg_idx = 0xffffffffu;
         for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++witer) {
             const int tile = w / P.splits;
             const int64_t row0 = (int64_t)tile * BM;
             const uint32_t buf = witer & 1u;
-            mbar_wait(L.wfull(buf), (witer >> 1) & 1u);
+            mbar_wait_sleep(L.wfull(buf), (witer >> 1) & 1u);
             const uint32_t n = ld_shared_u32(L.count(buf));
             const uint32_t nfill = (n + Q - 1) / Q;
-            uint32_t prev_sk = 0xffffffffu, prev_s = 0xffffffffu;
-            uint64_t seg_src = 0;
-            uint32_t seg_stride = 0, seg_idx = 0xffffffffu;
-            uint64_t rp[NI];
-            uint32_t vmask = 0;
             while (my_next < c0 + nfill) {
-                const uint32_t j0 = (my_next - c0) * Q;
-                const uint32_t cnt = min(Q, n - j0);
+                const uint32_t j = (my_next - c0) * Q + gw;     // my chunk of this fill (if j < n)
+                const bool have = j < n;
+                uint32_t e = 0;
+                if (have) e = ld_shared_u32(L.list(buf, (int)j));
+                const uint32_t s = e >> 8, k = (e >> 3) & 31u, kb = e & 7u;
+                if (have && s != prev_s) {     // segment constants (rarely changes)
+                    prev_s = s;
+                    const uint2 sa = ld_shared_u2(L.segtab + 32 * s);
+                    const uint2 sb = ld_shared_u2(L.segtab + 32 * s + 16);
+                    seg_src = ((uint64_t)sa.y << 32 | sa.x) + (uint32_t)(chunk * 16);
+                    seg_stride = sb.x;
+                    seg_idx = ld_shared_u32(L.segtab + 32 * s + 24);
+                }
                 mbar_wait(L.empty(slot), phase ^ 1u);
-                for (uint32_t qi = 0; qi < cnt; ++qi) {
-                    const uint32_t e = ld_shared_u32(L.list(buf, (int)(j0 + qi)));
-                    const uint32_t kb = e & 7u;
-                    if ((e >> 3) != prev_sk) {     // new (segment, offset): source addresses of my NI (row, 16 B chunk) slots
-                        prev_sk = e >> 3;
-                        const uint32_t s = e >> 8, k = (e >> 3) & 31u;
-                        if (s != prev_s) {
-                            prev_s = s;
-                            const uint2 sa = ld_shared_u2(L.segtab + 32 * s);
-                            const uint2 sb = ld_shared_u2(L.segtab + 32 * s + 16);
-                            seg_src = ((uint64_t)sa.y << 32 | sa.x) + (uint32_t)(chunk * 16);
-                            seg_stride = sb.x;
-                            seg_idx = ld_shared_u32(L.segtab + 32 * s + 24);
+                if (have && !(P.debug & 2)) {
+                    const uint64_t src0 = seg_src + kb * ROW;
+                    const uint32_t dst0 = L.a(slot * Q + gw);
+                    // absent neighbours: either a zero-filled copy (src-size 0) or a read of one of 256 spread-out zero rows
+                    const uint64_t zsrc0 = zero_src + kb * ROW;
+                    const uint32_t zr0 = (uint32_t)tile * 37u + (uint32_t)sub * 16u;
+                    if (seg_idx != 0xffffffffu) {
+                        const uint32_t ia = L.idx(buf, (int)(seg_idx + k), sub);
+                        if (P.zero_row)
+                            gather_rows<EB, 2>(ia, dst0, a_off_even, a_off_odd, src0, seg_stride, zsrc0, zr0);
+                        else if (P.use_cg)
+                            gather_rows<EB, 0>(ia, dst0, a_off_even, a_off_odd, src0, seg_stride, zsrc0, zr0);
+                        else
+                            gather_rows<EB, 1>(ia, dst0, a_off_even, a_off_odd, src0, seg_stride, zsrc0, zr0);
+                    } else {   // identity segment (1x1 projection / residual input): row = tile row
+#pragma unroll 4
+                        for (int i = 0; i < NR; ++i) {
+                            const int64_t row = row0 + i * RPI + sub;
+                            const uint32_t dst = dst0 + (uint32_t)(i * RPI * ROW) + ((i & 1) ? a_off_odd : a_off_even);
+                            const uint64_t src = src0 + (uint64_t)(uint32_t)(row < d.n_out ? row : 0) * seg_stride;
+                            cp_async16_cg(dst, reinterpret_cast<const void*>(src), row < d.n_out ? 16u : 0u);
                         }
-                        vmask = 0;
-#pragma unroll
-                        for (int i = 0; i < NI; ++i) {
-                            int r;
-                            if (seg_idx != 0xffffffffu) r = ld_shared_i32(L.idx(buf, (int)(seg_idx + k), my_col + i * RPI));
-                            else r = (row0 + my_col + i * RPI) < d.n_out ? (int)(row0 + my_col + i * RPI) : -1;
-                            vmask |= (r >= 0 ? 1u : 0u) << i;
-                            rp[i] = seg_src + (uint64_t)(uint32_t)max(r, 0) * seg_stride;   // absent: zero-filled copy (src-size 0)
-                        }
-                    }
-                    const uint32_t a_st = L.a(slot * Q + qi);
-                    const uint32_t koff = kb * ROW;
-                    if (P.debug & 2) {
-                    } else if (P.use_cg) {
-#pragma unroll
-                        for (int i = 0; i < NI; ++i)
-                            cp_async16_cg(a_st + a_off[i], reinterpret_cast<const void*>(rp[i] + koff),
-                                          ((vmask >> i) & 1u) ? 16u : 0u);
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < NI; ++i)
-                            cp_async16(a_st + a_off[i], reinterpret_cast<const void*>(rp[i] + koff),
-                                       ((vmask >> i) & 1u) ? 16u : 0u);
                     }
                 }
                 cp_async_mbar_arrive_noinc(L.full(slot));
@@ -524,25 +575,27 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const tl_conv_desc d, c
             uint32_t slot = 0, phase = 0, witer = 0;
             for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++witer) {
                 const uint32_t buf = witer & 1u;
-                mbar_wait(L.wfull(buf), (witer >> 1) & 1u);
+                mbar_wait_sleep(L.wfull(buf), (witer >> 1) & 1u);
                 const uint32_t n = ld_shared_u32(L.count(buf));
                 for (uint32_t j0 = 0; j0 < n; j0 += Q) {
                     const uint32_t cnt = min(Q, n - j0);
+                    // lane qi prepares chunk qi's slab address while the slot drains; one elected lane then issues the copies
+                    uint64_t wsrc = 0;
+                    if ((uint32_t)lane < cnt) {
+                        const uint32_t e = ld_shared_u32(L.list(buf, (int)(j0 + lane)));
+                        const uint32_t s = e >> 8, k = (e >> 3) & 31u, kb = e & 7u;
+                        const uint64_t wb = s == 0 ? wbase[0] : (s == 1 ? wbase[1] : wbase[2]);
+                        const uint32_t kbs = s == 0 ? wkb[0] : (s == 1 ? wkb[1] : wkb[2]);
+                        wsrc = wb + (uint64_t)(k * kbs + kb) * slab;
+                    }
                     mbar_wait(L.empty(slot), phase ^ 1u);
-                    if (elect_one()) {
-                        if (P.debug & 8) {
-                            mbar_arrive(L.full(slot));
-                        } else {
-                            mbar_arrive_expect_tx(L.full(slot), cnt * slab);
-                            for (uint32_t qi = 0; qi < cnt; ++qi) {
-                                const uint32_t e = ld_shared_u32(L.list(buf, (int)(j0 + qi)));
-                                const uint32_t s = e >> 8, k = (e >> 3) & 31u, kb = e & 7u;
-                                const uint64_t wb = s == 0 ? wbase[0] : (s == 1 ? wbase[1] : wbase[2]);
-                                const uint32_t kbs = s == 0 ? wkb[0] : (s == 1 ? wkb[1] : wkb[2]);
-                                bulk_g2s(L.b(slot * Q + qi), reinterpret_cast<const void*>(wb + (uint64_t)(k * kbs + kb) * slab),
-                                         slab, L.full(slot));
-                            }
-                        }
+                    if (P.debug & 8) {
+                        if (lane == 0) mbar_arrive(L.full(slot));
+                    } else {
+                        if (lane == 0) mbar_arrive_expect_tx(L.full(slot), cnt * slab);
+                        __syncwarp();
+                        if ((uint32_t)lane < cnt)
+                            bulk_g2s(L.b(slot * Q + lane), reinterpret_cast<const void*>(wsrc), slab, L.full(slot));
                     }
                     __syncwarp();
                     if (++slot == S) slot = 0, phase ^= 1u;
@@ -560,15 +613,30 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const tl_conv_desc d, c
         for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++titer) {
             const int tile = w / P.splits;
             const uint32_t buf = titer & 1u;
-            mbar_wait(L.wfull(buf), (titer >> 1) & 1u);
+            mbar_wait_sleep(L.wfull(buf), (titer >> 1) & 1u);
             const bool any = ld_shared_u32(L.count(buf)) != 0u;
             mbar_arrive(L.wempty(buf));
-            mbar_wait(L.tfull(buf), (titer >> 1) & 1u);
-            tc_fence_after();
             const int64_t wrow0 = (int64_t)tile * BM + ew * 32;   // first row of this warp's quarter
+            // residual rows of the first 32-column block are fetched BEFORE waiting for the accumulator: their DRAM
+            // latency (8 dependent ~1 us loads per tile when issued inside the store loop) hides behind the main loop
+            const bool has_res = d.residual != nullptr && P.splits == 1 && !(P.debug & 4);
+            float4 res[8];
+            auto fetch_residual = [&](int c0) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int64_t grow = wrow0 + i * 4 + rsub;
+                    res[i] = (has_res && grow < d.n_out)
+                                 ? __ldg(reinterpret_cast<const float4*>(d.residual + grow * N + c0 + 4 * cc))
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            };
+            fetch_residual(0);
+            mbar_wait_sleep(L.tfull(buf), (titer >> 1) & 1u);
+            tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + buf * P.buf_cols;
             if (any || P.splits == 1) {
                 for (int c0 = 0; c0 < N; c0 += 32) {
+                    if (c0 > 0) fetch_residual(c0);     // in flight during the TMEM load + transpose of this block
                     uint32_t acc[32];
                     if (any) {
                         tmem_ld32(taddr + c0, acc);
@@ -605,10 +673,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const tl_conv_desc d, c
                                          : "memory");
                             continue;
                         }
-                        if (d.residual) {
-                            const float4 r4 = __ldg(reinterpret_cast<const float4*>(d.residual + o));
-                            v.x += r4.x, v.y += r4.y, v.z += r4.z, v.w += r4.w;
-                        }
+                        v.x += res[i].x, v.y += res[i].y, v.z += res[i].z, v.w += res[i].w;
                         if (d.out_raw) *reinterpret_cast<float4*>(d.out_raw + o) = v;
                         if (d.out_act1) {
                             const float a0 = fmaxf(fmaf(v.x, s1.x, t1.x), 0.f), a1 = fmaxf(fmaf(v.y, s1.y, t1.y), 0.f);
@@ -637,11 +702,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const tl_conv_desc d, c
             uint32_t slot = 0, phase = 0, titer = 0;
             for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++titer) {
                 const uint32_t buf = titer & 1u;
-                mbar_wait(L.wfull(buf), (titer >> 1) & 1u);
+                mbar_wait_sleep(L.wfull(buf), (titer >> 1) & 1u);
                 const uint32_t n = ld_shared_u32(L.count(buf));
                 __syncwarp();
                 if (elect_one()) mbar_arrive(L.wempty(buf));
-                mbar_wait(L.tempty(buf), ((titer >> 1) & 1u) ^ 1u);
+                mbar_wait_sleep(L.tempty(buf), ((titer >> 1) & 1u) ^ 1u);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + buf * P.buf_cols;
                 for (uint32_t j0 = 0; j0 < n; j0 += Q) {
@@ -710,42 +775,75 @@ __global__ void k_splitk_epilogue(const tl_conv_desc d, const float* __restrict_
 template <int EB>
 __global__ void __launch_bounds__(128) k_conv_in4(const tl_conv_desc d) {
     __shared__ __align__(16) float ws[27 * 4 * 32];
+    __shared__ __align__(16) float stage[4][32 * 32];     // per warp: 32 rows x 32 columns, transposed for coalesced stores
     const tl_conv_seg& sg = d.seg[0];
     for (int e = threadIdx.x; e < sg.n_off * 4 * 32; e += blockDim.x) ws[e] = sg.weight[e];
     __syncthreads();
-    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t mask = seg_mask(sg, r / TL_TILE_ROWS);
-    if (r >= d.n_out) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t wrow0 = (int64_t)blockIdx.x * blockDim.x + warp * 32;
+    const int64_t r = wrow0 + lane;
+    const bool live = r < d.n_out;
+    const uint32_t mask = live ? seg_mask(sg, r / TL_TILE_ROWS) : 0u;
     float acc[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) acc[j] = 0.f;
-    for (int k = 0; k < sg.n_off; ++k) {
-        if (!((mask >> k) & 1u)) continue;
-        const int src = __ldg(sg.index + (int64_t)k * sg.index_stride + r);
-        if (src < 0) continue;
-        const float4 x = __ldg(reinterpret_cast<const float4*>(sg.src + (int64_t)src * sg.src_stride));
-        const float4* w4 = reinterpret_cast<const float4*>(ws + k * 128);
+    // offsets in groups of 9: all rulebook entries, then all gathered rows (independent loads in flight), then the FMAs
+    for (int g = 0; g < 27; g += 9) {
+        int src[9];
+        float4 x[9];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float4 w0 = w4[j], w1 = w4[8 + j], w2 = w4[16 + j], w3 = w4[24 + j];
-            acc[4 * j] += x.x * w0.x + x.y * w1.x + x.z * w2.x + x.w * w3.x;
-            acc[4 * j + 1] += x.x * w0.y + x.y * w1.y + x.z * w2.y + x.w * w3.y;
-            acc[4 * j + 2] += x.x * w0.z + x.y * w1.z + x.z * w2.z + x.w * w3.z;
-            acc[4 * j + 3] += x.x * w0.w + x.y * w1.w + x.z * w2.w + x.w * w3.w;
+        for (int j = 0; j < 9; ++j) {
+            const int k = g + j;
+            src[j] = (k < sg.n_off && ((mask >> k) & 1u)) ? __ldg(sg.index + (int64_t)k * sg.index_stride + r) : -1;
+        }
+#pragma unroll
+        for (int j = 0; j < 9; ++j)
+            x[j] = src[j] >= 0 ? __ldg(reinterpret_cast<const float4*>(sg.src + (int64_t)src[j] * sg.src_stride))
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+            if (src[j] < 0) continue;
+            const float4* w4 = reinterpret_cast<const float4*>(ws + (g + j) * 128);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float4 w0 = w4[c], w1 = w4[8 + c], w2 = w4[16 + c], w3 = w4[24 + c];
+                acc[4 * c] += x[j].x * w0.x + x[j].y * w1.x + x[j].z * w2.x + x[j].w * w3.x;
+                acc[4 * c + 1] += x[j].x * w0.y + x[j].y * w1.y + x[j].z * w2.y + x[j].w * w3.y;
+                acc[4 * c + 2] += x[j].x * w0.z + x[j].y * w1.z + x[j].z * w2.z + x[j].w * w3.z;
+                acc[4 * c + 3] += x[j].x * w0.w + x[j].y * w1.w + x[j].z * w2.w + x[j].w * w3.w;
+            }
         }
     }
-    const int64_t o = r * 32;
-    if (d.residual) {
+    // row `lane` -> shared (16 B chunk j at j ^ (lane & 7)), then every store instruction covers whole 128 B lines
+    float* st = stage[warp];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc[j] += __ldg(d.residual + o + j);
-    }
-    if (d.out_raw) {
-        float4* op = reinterpret_cast<float4*>(d.out_raw + o);
+    for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(st + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+            make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+    __syncwarp();
+    const int cc = lane & 7, rsub = lane >> 3, col = 4 * cc;
+    float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), t1 = s1, s2 = s1, t2 = s1;
+    if (d.out_act1) s1 = __ldg(reinterpret_cast<const float4*>(d.scale1 + col)), t1 = __ldg(reinterpret_cast<const float4*>(d.shift1 + col));
+    if (d.out_act2) s2 = __ldg(reinterpret_cast<const float4*>(d.scale2 + col)), t2 = __ldg(reinterpret_cast<const float4*>(d.shift2 + col));
 #pragma unroll
-        for (int j = 0; j < 8; ++j) op[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+    for (int i = 0; i < 8; ++i) {
+        const int rr = i * 4 + rsub;
+        float4 v = *reinterpret_cast<const float4*>(st + rr * 32 + ((cc ^ (rr & 7)) << 2));
+        const int64_t grow = wrow0 + rr;
+        if (grow >= d.n_out) continue;
+        const int64_t o = grow * 32 + col;
+        if (d.residual) {
+            const float4 r4 = __ldg(reinterpret_cast<const float4*>(d.residual + o));
+            v.x += r4.x, v.y += r4.y, v.z += r4.z, v.w += r4.w;
+        }
+        if (d.out_raw) *reinterpret_cast<float4*>(d.out_raw + o) = v;
+        if (d.out_act1)
+            store_act4<EB>(d.out_act1, o, fmaxf(fmaf(v.x, s1.x, t1.x), 0.f), fmaxf(fmaf(v.y, s1.y, t1.y), 0.f),
+                           fmaxf(fmaf(v.z, s1.z, t1.z), 0.f), fmaxf(fmaf(v.w, s1.w, t1.w), 0.f));
+        if (d.out_act2)
+            store_act4<EB>(d.out_act2, o, fmaxf(fmaf(v.x, s2.x, t2.x), 0.f), fmaxf(fmaf(v.y, s2.y, t2.y), 0.f),
+                           fmaxf(fmaf(v.z, s2.z, t2.z), 0.f), fmaxf(fmaf(v.w, s2.w, t2.w), 0.f));
     }
-    if (d.out_act1) store_act32<EB>(d.out_act1, o, acc, d.scale1, d.shift1);
-    if (d.out_act2) store_act32<EB>(d.out_act2, o, acc, d.scale2, d.shift2);
 }
 
 }  // namespace tc
@@ -755,7 +853,7 @@ int conv_fwd_simt(const tl_conv_desc& d, cudaStream_t stream);
 static bool tc_eligible(const tl_conv_desc& d) {
     if (d.c_out % 32 != 0 || d.c_out > 256) return false;
     for (int s = 0; s < d.n_seg; ++s)
-        if (d.seg[s].c_in % tc::BK != 0 || d.seg[s].src_stride % 4 != 0) return false;
+        if (d.seg[s].c_in % tc::BK != 0 || d.seg[s].c_in > 8 * tc::BK || d.seg[s].src_stride % 4 != 0) return false;
     return true;
 }
 
@@ -801,7 +899,7 @@ int conv_fwd_tc(const tl_conv_desc& d, cudaStream_t stream, bool half) {
     P.acc_cols = 32;
     while (P.acc_cols < n) P.acc_cols <<= 1;
     P.debug = env_int("TL_TC_DEBUG", 0);
-    P.acc_ways = env_int("TL_TC_WAYS", 4);
+    P.acc_ways = env_int("TL_TC_WAYS", 1);
     while (P.acc_ways > 1 && (2 * P.acc_ways * P.acc_cols > 512 || P.acc_ways > row_bytes / 32)) P.acc_ways >>= 1;
     P.buf_cols = P.acc_ways * P.acc_cols;
     P.tmem_cols = 2 * P.buf_cols;  // <= 512
@@ -810,6 +908,8 @@ int conv_fwd_tc(const tl_conv_desc& d, cudaStream_t stream, bool half) {
     const size_t sub = (size_t)(tc::BM + n) * row_bytes;
     const int ring_budget = smem_budget - 2048 - 2 * tc::IDX_BUF_BYTES - tc::EPI_BYTES;
     int q = env_int("TL_TC_Q", 4);
+    if (q > 8) q = 8;
+    while (q & (q - 1)) --q;   // power of two
     while (q > 1 && (size_t)ring_budget / (q * sub) < 3) q >>= 1;
     int stages = (int)(ring_budget / (q * sub));
     if (stages < 2) stages = 2;
@@ -818,10 +918,14 @@ int conv_fwd_tc(const tl_conv_desc& d, cudaStream_t stream, bool half) {
     P.stages = stages;
     P.q = q;
     // the producer groups take the CTA's slot fills round-robin; G <= stages keeps the ring deadlock-free
-    int groups = env_int("TL_TC_GROUPS", tc::kMaxGroups);
-    while (groups > 1 && (groups > stages || groups > tc::kMaxGroups)) groups >>= 1;
+    int groups = env_int("TL_TC_GROUPS", tc::kProducerWarps / q);   // a group = q warps (one per chunk of a slot)
+    if (groups > tc::kProducerWarps / q) groups = tc::kProducerWarps / q;
+    if (groups > stages) groups = stages;
+    if (groups < 1) groups = 1;
     P.groups = groups;
     P.use_cg = env_int("TL_TC_CG", 1);
+    P.zero_row = env_int("TL_TC_ZERO_ROW", 1);
+    P.prefetch = env_int("TL_TC_PREFETCH", 1);
     const size_t smem = tc::smem_bytes(n, stages * q, row_bytes);
     P.num_tiles = (d.n_out + tc::BM - 1) / tc::BM;
     P.chunks_total = 0;
@@ -839,8 +943,11 @@ int conv_fwd_tc(const tl_conv_desc& d, cudaStream_t stream, bool half) {
         else P.idx_base[s] = idx_rows, P.idx_owner[s] = 1, idx_rows += d.seg[s].n_off;
     }
     if (idx_rows > tc::IDX_ROWS || P.chunks_total > tc::MAX_CHUNKS) return conv_fwd_simt_fallback_note(d, stream);
-    for (int s = 0; s < d.n_seg; ++s)
+    for (int s = 0; s < d.n_seg; ++s) {
         TL_REQUIRE(!d.seg[s].index || d.seg[s].index_stride % 4 == 0, "tl_conv_fwd(tf32): index_stride must be a multiple of 4");
+        TL_REQUIRE(d.seg[s].c_in <= 8 * tc::BK, "tl_conv_fwd(tcgen05): segment %d has c_in=%d > 256 (split it into two segments)",
+                   s, d.seg[s].c_in);
+    }
     P.splits = 1;
     P.splitk_ws = nullptr;
     if (d.splitk_ws && P.num_tiles < split_target * num_sms) {

@@ -10,7 +10,7 @@
 namespace tl {
 namespace train {
 
-constexpr int kMaxCB = 8;   // column blocks of 32: channels <= 256
+constexpr int kMaxCB = 16;  // column blocks of 32: channels <= 512 (the widest BatchNorm sees the 2 x 192 skip concat)
 
 // per-channel sum and sum of squares of x [n, c] -> acc[0..c) += sum, acc[c..2c) += sumsq (fp64 atomics)
 __global__ void __launch_bounds__(256) k_bn_stats(const float* __restrict__ x, int64_t n, int c, int rows_per_block,

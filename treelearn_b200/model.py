@@ -233,11 +233,22 @@ class TreeLearn(nn.Module):
 
     def _train_residual(self, p, x, geom, mode):
         from . import autograd as ag
-        h = ag.sparse_conv(ag.bn_relu(x, self._get(p + '.conv_branch.0')), self._get(p + '.conv_branch.2').weight, geom, mode)
-        h = ag.sparse_conv(ag.bn_relu(h, self._get(p + '.conv_branch.3')), self._get(p + '.conv_branch.5').weight, geom, mode)
+
+        def conv(a, weight, g):
+            """Inputs wider than the conv's output (the 2C skip concat of blocks_tail.block0) run as two convs over the
+            channel halves: the kernels take at most 256 channels per operand, and the halves are what the fused inference
+            schedule feeds as two segments anyway."""
+            ci, co = weight.shape[-1], weight.shape[0]
+            if ci == 2 * co:
+                return (ag.sparse_conv(a[:, :co].contiguous(), weight[..., :co], g, mode) +
+                        ag.sparse_conv(a[:, co:].contiguous(), weight[..., co:], g, mode))
+            return ag.sparse_conv(a, weight, g, mode)
+
+        h = conv(ag.bn_relu(x, self._get(p + '.conv_branch.0')), self._get(p + '.conv_branch.2').weight, geom)
+        h = conv(ag.bn_relu(h, self._get(p + '.conv_branch.3')), self._get(p + '.conv_branch.5').weight, geom)
         blk = self._get(p)
         if 'i_branch' in blk._modules:   # 1x1 projection of the residual branch (reference blocks.py:29-39)
-            x = ag.sparse_conv(x, self._get(p + '.i_branch.0').weight, ag.identity_geom(x.shape[0]), mode)
+            x = conv(x, self._get(p + '.i_branch.0').weight, ag.identity_geom(x.shape[0]))
         return h + x
 
     def _train_ublock(self, p, l, x, geoms, mode):
@@ -337,7 +348,7 @@ def point_wise_loss(semantic_prediction_logits, offset_predictions, masks_sem, m
 
 def tc_eligible(c_in, c_out):
     """Same rule as csrc/tl_conv_tc.cu: the tcgen05 path takes 32-channel K blocks and N = C_out <= 256."""
-    return c_in % 32 == 0 and c_out % 32 == 0 and c_out <= 256
+    return c_in % 32 == 0 and c_in <= 256 and c_out % 32 == 0 and c_out <= 256
 
 
 def _round_tf32(w):
