@@ -38,7 +38,8 @@ constexpr int kWeightWarp = kProducerWarps + 6;         // 18: one thread bulk-c
 constexpr int kThreads = 32 * (kProducerWarps + 4 + 3);
 constexpr int MAX_CHUNKS = 448;                         // live (segment, offset, k-block) entries per work item
 constexpr int IDX_ROWS = 32;                         // rulebook rows (segment, offset) staged per tile
-constexpr int IDX_BUF_BYTES = IDX_ROWS * BM * 4 + MAX_CHUNKS * 4 + 64;   // rulebook rows + chunk list + count; x2
+constexpr int IDX_BUF_BYTES = IDX_ROWS * BM * 4 + MAX_CHUNKS * 4 + 64;   // rulebook rows + chunk list + count
+constexpr int NDESC = 3;                             // work-item descriptors in flight: the scheduler runs NDESC-1 items ahead
 constexpr int EPI_BYTES = 4 * 32 * 128;              // per epilogue warp: 32 rows x 32 fp32 columns, transposed for coalescing
 constexpr int SEGTAB_BYTES = 32 * TL_MAX_SEG;
 
@@ -69,7 +70,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 // per-tile waits (descriptor / accumulator hand-offs) back off between polls so that they do not steal issue slots
 // from the gather warps (measured: 20 % of all issued instructions were try_wait spins)
-__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, uint32_t ns) {
     uint32_t done = 0;
     while (true) {
         asm volatile(
@@ -82,7 +83,7 @@ __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
             : "r"(bar), "r"(parity)
             : "memory");
         if (done) break;
-        __nanosleep(64);
+        if (ns) __nanosleep(ns);
     }
 }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
@@ -163,6 +164,27 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
         "}\n" ::"r"(tmem_d),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// accumulate-always forms (enable_input_d = true folds to the constant predicate: no setp / predicate moves per MMA)
+__device__ __forceinline__ void umma_tf32_acc(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.eq.u32 p, 1, 1;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f16_acc(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.eq.u32 p, 1, 1;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc)
         : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -279,6 +301,7 @@ struct Launch {   // per-launch scalars (kernel parameter)
     float* splitk_ws;  // [n_out, c_out] zeroed fp32 accumulation buffer when splits > 1
     int groups;        // active producer groups (power of two <= kMaxGroups, < stages)
     int use_cg;        // gather A rows with cp.async.cg (bypass L1) instead of .ca
+    int sleep_ns;      // back-off of the per-tile barrier waits (0 = spin)
     int prefetch;      // 1: the scheduler bulk-prefetches (L2) the tile's own source rows of submanifold / identity segments
     int zero_row;      // 1: absent neighbours read a zero row (every copy a uniform 16 B); 0: cp.async zero-fill (src-size 0)
     int idx_base[TL_MAX_SEG];   // first prefetch row of each indexed segment (segments sharing a table share rows); -1 = identity
@@ -297,8 +320,8 @@ struct Layout {  // dynamic shared memory carve-up (1024 B aligned base)
     __device__ __forceinline__ uint32_t empty(uint32_t s) const { return empty0 + 8 * s; }
     __device__ __forceinline__ uint32_t tfull(uint32_t b) const { return tfull0 + 8 * b; }
     __device__ __forceinline__ uint32_t tempty(uint32_t b) const { return tempty0 + 8 * b; }
-    __device__ __forceinline__ uint32_t wfull(uint32_t b) const { return tempty0 + 16 + 8 * b; }
-    __device__ __forceinline__ uint32_t wempty(uint32_t b) const { return tempty0 + 32 + 8 * b; }
+    __device__ __forceinline__ uint32_t wfull(uint32_t b) const { return tempty0 + 16 + 8 * b; }              // NDESC
+    __device__ __forceinline__ uint32_t wempty(uint32_t b) const { return tempty0 + 16 + 8 * NDESC + 8 * b; }  // NDESC
     __device__ __forceinline__ uint32_t list(uint32_t buf, int j) const {
         return idx0 + buf * IDX_BUF_BYTES + IDX_ROWS * BM * 4 + (uint32_t)j * 4u;
     }
@@ -314,19 +337,19 @@ __device__ __forceinline__ Layout carve(uint32_t base, int n, int substages, int
     L.b0 = base + substages * L.a_stage_bytes;
     L.b_stage_bytes = n * row_bytes;
     L.idx0 = L.b0 + substages * L.b_stage_bytes;
-    L.epi0 = L.idx0 + 2 * IDX_BUF_BYTES;
+    L.epi0 = L.idx0 + NDESC * IDX_BUF_BYTES;
     uint32_t off = L.epi0 + EPI_BYTES;
     L.full0 = off;
     L.empty0 = off + 8 * MAX_STAGES;
     L.tfull0 = off + 16 * MAX_STAGES;
     L.tempty0 = L.tfull0 + 16;
-    L.tmem_slot = L.tfull0 + 64;
-    L.segtab = L.tfull0 + 96;
+    L.tmem_slot = L.tfull0 + 32 + 16 * NDESC;
+    L.segtab = L.tfull0 + 64 + 16 * NDESC;
     return L;
 }
 static inline size_t smem_bytes(int n, int substages, int row_bytes) {
-    return 1024 + (size_t)substages * ((size_t)BM * row_bytes + (size_t)n * row_bytes) + 2 * IDX_BUF_BYTES + EPI_BYTES +
-           16 * MAX_STAGES + 96 + SEGTAB_BYTES + 32;
+    return 1024 + (size_t)substages * ((size_t)BM * row_bytes + (size_t)n * row_bytes) + NDESC * IDX_BUF_BYTES + EPI_BYTES +
+           16 * MAX_STAGES + 64 + 16 * NDESC + SEGTAB_BYTES + 32;
 }
 
 __device__ __forceinline__ uint32_t seg_mask(const tl_conv_seg& sg, int64_t tile) {
@@ -405,6 +428,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const tl_conv_desc d, c
         for (int b = 0; b < 2; ++b) {
             mbar_init(L.tfull(b), 1);
             mbar_init(L.tempty(b), kEpilogueThreads);
+        }
+        for (int b = 0; b < NDESC; ++b) {
             mbar_init(L.wfull(b), 33);                               // 32 cp.async completions + lane 0
             mbar_init(L.wempty(b), 32 * P.q * P.groups + kEpilogueThreads + 2);   // every reader of the descriptor
         }
@@ -433,8 +458,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const tl_conv_desc d, c
         // ===================== scheduler: work-item descriptors ====================================
         uint32_t witer = 0;
         for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++witer) {
-            const uint32_t buf = witer & 1u;
-            if (witer >= 2) mbar_wait_sleep(L.wempty(buf), ((witer >> 1) - 1u) & 1u);   // readers of item witer-2 are done
+            const uint32_t buf = witer % NDESC;
+            if (witer >= NDESC) mbar_wait_sleep(L.wempty(buf), ((witer / NDESC) - 1u) & 1u, (uint32_t)P.sleep_ns);   // readers of item witer-NDESC are done
             const int tile = w / P.splits, split = w - tile * P.splits;
             const int lo = split * per_split, hi = min(lo + per_split, P.chunks_total);
             int ord = 0, pos = 0;
@@ -508,8 +533,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const tl_conv_desc d, c
         for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++witer) {
             const int tile = w / P.splits;
             const int64_t row0 = (int64_t)tile * BM;
-            const uint32_t buf = witer & 1u;
-            mbar_wait_sleep(L.wfull(buf), (witer >> 1) & 1u);
+            const uint32_t buf = witer % NDESC;
+            mbar_wait_sleep(L.wfull(buf), (witer / NDESC) & 1u, (uint32_t)P.sleep_ns);
             const uint32_t n = ld_shared_u32(L.count(buf));
             const uint32_t nfill = (n + Q - 1) / Q;
             while (my_next < c0 + nfill) {
@@ -574,8 +599,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const tl_conv_desc d, c
             }
             uint32_t slot = 0, phase = 0, witer = 0;
             for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++witer) {
-                const uint32_t buf = witer & 1u;
-                mbar_wait_sleep(L.wfull(buf), (witer >> 1) & 1u);
+                const uint32_t buf = witer % NDESC;
+                mbar_wait_sleep(L.wfull(buf), (witer / NDESC) & 1u, (uint32_t)P.sleep_ns);
                 const uint32_t n = ld_shared_u32(L.count(buf));
                 for (uint32_t j0 = 0; j0 < n; j0 += Q) {
                     const uint32_t cnt = min(Q, n - j0);
@@ -612,10 +637,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const tl_conv_desc d, c
         uint32_t titer = 0;
         for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++titer) {
             const int tile = w / P.splits;
-            const uint32_t buf = titer & 1u;
-            mbar_wait_sleep(L.wfull(buf), (titer >> 1) & 1u);
-            const bool any = ld_shared_u32(L.count(buf)) != 0u;
-            mbar_arrive(L.wempty(buf));
+            const uint32_t buf = titer & 1u;          // TMEM accumulator buffer
+            const uint32_t dbuf = titer % NDESC;      // work-item descriptor buffer
+            mbar_wait_sleep(L.wfull(dbuf), (titer / NDESC) & 1u, (uint32_t)P.sleep_ns);
+            const bool any = ld_shared_u32(L.count(dbuf)) != 0u;
+            mbar_arrive(L.wempty(dbuf));
             const int64_t wrow0 = (int64_t)tile * BM + ew * 32;   // first row of this warp's quarter
             // residual rows of the first 32-column block are fetched BEFORE waiting for the accumulator: their DRAM
             // latency (8 dependent ~1 us loads per tile when issued inside the store loop) hides behind the main loop
@@ -631,7 +657,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const tl_conv_desc d, c
                 }
             };
             fetch_residual(0);
-            mbar_wait_sleep(L.tfull(buf), (titer >> 1) & 1u);
+            mbar_wait_sleep(L.tfull(buf), (titer >> 1) & 1u, (uint32_t)P.sleep_ns);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + buf * P.buf_cols;
             if (any || P.splits == 1) {
@@ -697,16 +723,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const tl_conv_desc d, c
         {
             const uint32_t idesc = make_idesc(N, EB == 2);
             const uint64_t adesc0 = make_smem_desc(L.a0, ROW), bdesc0 = make_smem_desc(L.b0, ROW);
-            const uint32_t a_step = L.a_stage_bytes >> 4, b_step = L.b_stage_bytes >> 4;
+            const uint32_t b_step = L.b_stage_bytes >> 4;
             const uint32_t wmask = (uint32_t)(P.acc_ways - 1);
             uint32_t slot = 0, phase = 0, titer = 0;
             for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++titer) {
-                const uint32_t buf = titer & 1u;
-                mbar_wait_sleep(L.wfull(buf), (titer >> 1) & 1u);
-                const uint32_t n = ld_shared_u32(L.count(buf));
+                const uint32_t buf = titer & 1u;          // TMEM accumulator buffer
+                const uint32_t dbuf = titer % NDESC;      // work-item descriptor buffer
+                mbar_wait_sleep(L.wfull(dbuf), (titer / NDESC) & 1u, (uint32_t)P.sleep_ns);
+                const uint32_t n = ld_shared_u32(L.count(dbuf));
                 __syncwarp();
-                if (elect_one()) mbar_arrive(L.wempty(buf));
-                mbar_wait_sleep(L.tempty(buf), ((titer >> 1) & 1u) ^ 1u);
+                if (elect_one()) mbar_arrive(L.wempty(dbuf));
+                mbar_wait_sleep(L.tempty(buf), ((titer >> 1) & 1u) ^ 1u, (uint32_t)P.sleep_ns);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + buf * P.buf_cols;
                 for (uint32_t j0 = 0; j0 < n; j0 += Q) {
@@ -715,20 +742,31 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const tl_conv_desc d, c
                     tc_fence_after();
                     if (elect_one()) {
                         if (!(P.debug & 1)) {
-                            uint64_t adesc = adesc0 + (uint64_t)(slot * Q * a_step);
+                            constexpr uint32_t A_STEP = (uint32_t)(BM * ROW) >> 4;   // descriptor address units (16 B) per chunk
+                            uint64_t adesc = adesc0 + (uint64_t)(slot * Q * A_STEP);
                             uint64_t bdesc = bdesc0 + (uint64_t)(slot * Q * b_step);
-                            for (uint32_t qi = 0; qi < cnt; ++qi, adesc += a_step, bdesc += b_step) {
+                            // chunk 0 of the fill may open the accumulator (first chunk of the work item) ...
 #pragma unroll
-                                for (int kk = 0; kk < KSTEPS; ++kk) {  // UMMA K step = 32 B (8 tf32 / 16 fp16): advance inside the swizzle atom
-                                    // K-step kk accumulates into its own TMEM tile kk % ways (the epilogue adds the tiles up)
+                            for (int kk = 0; kk < KSTEPS; ++kk) {  // UMMA K step = 32 B (8 tf32 / 16 fp16): advance inside the swizzle atom
+                                // K-step kk accumulates into its own TMEM tile kk % ways (the epilogue adds the tiles up)
+                                const uint32_t way = (uint32_t)kk & wmask;
+                                const uint32_t accum = (j0 == 0 && (uint32_t)kk <= wmask) ? 0u : 1u;
+                                if (EB == 4)
+                                    umma_tf32(tmem_d + way * P.acc_cols, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, accum);
+                                else
+                                    umma_f16(tmem_d + way * P.acc_cols, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, accum);
+                            }
+                            // ... every later chunk accumulates
+                            for (uint32_t qi = 1; qi < cnt; ++qi) {
+                                adesc += A_STEP;
+                                bdesc += b_step;
+#pragma unroll
+                                for (int kk = 0; kk < KSTEPS; ++kk) {
                                     const uint32_t way = (uint32_t)kk & wmask;
-                                    const uint32_t accum = (j0 + qi == 0 && (uint32_t)kk <= wmask) ? 0u : 1u;
                                     if (EB == 4)
-                                        umma_tf32(tmem_d + way * P.acc_cols, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2),
-                                                  idesc, accum);
+                                        umma_tf32_acc(tmem_d + way * P.acc_cols, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc);
                                     else
-                                        umma_f16(tmem_d + way * P.acc_cols, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2),
-                                                 idesc, accum);
+                                        umma_f16_acc(tmem_d + way * P.acc_cols, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc);
                                 }
                             }
                         }
@@ -906,7 +944,7 @@ int conv_fwd_tc(const tl_conv_desc& d, cudaStream_t stream, bool half) {
     // ring = `stages` slots of `q` chunks each (a chunk = 128 gathered rows + the [C_out x 32] weight slab); one barrier
     // round trip hands over a whole slot, so the single-warp MMA / weight-loader loops pay their fixed cost once per q chunks
     const size_t sub = (size_t)(tc::BM + n) * row_bytes;
-    const int ring_budget = smem_budget - 2048 - 2 * tc::IDX_BUF_BYTES - tc::EPI_BYTES;
+    const int ring_budget = smem_budget - 2048 - tc::NDESC * tc::IDX_BUF_BYTES - tc::EPI_BYTES;
     int q = env_int("TL_TC_Q", 4);
     if (q > 8) q = 8;
     while (q & (q - 1)) --q;   // power of two
@@ -926,6 +964,7 @@ int conv_fwd_tc(const tl_conv_desc& d, cudaStream_t stream, bool half) {
     P.use_cg = env_int("TL_TC_CG", 1);
     P.zero_row = env_int("TL_TC_ZERO_ROW", 1);
     P.prefetch = env_int("TL_TC_PREFETCH", 1);
+    P.sleep_ns = env_int("TL_TC_SLEEP", 64);
     const size_t smem = tc::smem_bytes(n, stages * q, row_bytes);
     P.num_tiles = (d.n_out + tc::BM - 1) / tc::BM;
     P.chunks_total = 0;
