@@ -142,6 +142,23 @@ int tl_knn_vote(const float* ref_xyz, const int64_t* ref_labels, int64_t n_ref, 
                 int64_t n_query, int32_t k, int64_t* out_labels, void* workspace, size_t workspace_bytes,
                 void* stream);
 
+/* ---- HDBSCAN(min_cluster_size = m) on 2-D points: replaces `group_hdbscan` -> sklearn.cluster.HDBSCAN
+ *      (tree_learn/util/pipeline.py:184-191; the DEFAULT clusterer, configs/_modular/grouping.yaml:7).
+ * tl_core_distance: core[i] = distance from point i to its k-th nearest neighbour, itself included (fp64, no FMA) --
+ *                   sklearn `_hdbscan_prims`: NearestNeighbors(n_neighbors=min_samples).kneighbors(X)[:, -1].
+ * tl_mst_prim:      minimum spanning tree of the mutual-reachability graph max(core_a, core_b, |a-b|), Prim's algorithm
+ *                   from node 0 with sklearn's tie rules (`mst_from_data_matrix`): edge i = (mst_src[i], mst_dst[i], mst_w[i])
+ *                   in the order Prim adds them.  One persistent cooperative kernel.
+ * tl_hdbscan_tree_labels: HOST arrays.  Edges sorted by weight (caller sorts) -> single linkage -> condensed tree ->
+ *                   stability -> excess-of-mass selection -> labels[n] (0.. in sklearn's numbering, -1 = noise). */
+size_t tl_hdbscan_workspace_bytes(int64_t n);
+int tl_core_distance(const float* points_xy, int64_t n, int32_t k, double* core, void* workspace, size_t workspace_bytes,
+                     void* stream);
+int tl_mst_prim(const float* points_xy, const double* core, int64_t n, int32_t* mst_src, int32_t* mst_dst, double* mst_w,
+                void* workspace, size_t workspace_bytes, void* stream);
+int tl_hdbscan_tree_labels(const int64_t* src, const int64_t* dst, const double* w, int64_t n, int64_t min_cluster_size,
+                           int64_t* labels);
+
 /* ---- training (SURVEY §8 a12 train mode, a16): BatchNorm1d(eps, momentum) with batch statistics applied to the
  *      feature rows of a sparse tensor + ReLU (tree_learn/model/tree_learn.py:34, blocks.py:57-70) and its backward,
  *      and the sparse-conv weight gradient (autograd through spconv in tools/training/train.py:40).

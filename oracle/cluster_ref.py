@@ -128,3 +128,162 @@ def assign_remaining_ref(coords, predictions, remaining_points_idx=-1, n_neighbo
         out[i] = vals[np.argmax(counts)]      # first max over sorted classes = smallest label on ties
     pred[q] = out
     return pred.astype(np.int64)
+
+
+# ---- HDBSCAN (reference util/pipeline.py:184-191 -> sklearn.cluster.HDBSCAN(min_cluster_size=m)) -----------------------
+# sklearn (>= 1.3; 1.9.0 in this image) is a third-party dependency of the reference; its algorithm for dense Euclidean
+# input is restated here (sklearn/cluster/_hdbscan/{hdbscan.py::_hdbscan_prims, _linkage.pyx, _tree.pyx}):
+#   core distance = distance to the min_samples-th neighbour incl. the point itself (min_samples = min_cluster_size),
+#   Prim MST of max(core_a, core_b, d_ab) from node 0, strict '<' relaxations, first minimal index wins,
+#   np.argsort of the edge weights, union-find dendrogram, condensed tree, stability, excess of mass, labelling.
+# Pinned against sklearn.cluster.HDBSCAN / the reference's group_hdbscan by tests/golden/make_golden_hdbscan.py.
+def core_distances_ref(points, k):
+    p = np.asarray(points, dtype=np.float64)
+    out = np.empty(len(p))
+    for i in range(len(p)):                      # d2 = dx*dx + dy*dy in fp64, like KDTree's reduced distance
+        d2 = (p[i, 0] - p[:, 0]) ** 2 + (p[i, 1] - p[:, 1]) ** 2
+        out[i] = np.sqrt(np.partition(d2, k - 1)[k - 1])
+    return out
+
+
+def prim_mst_ref(points, core):
+    p = np.asarray(points, dtype=np.float64)
+    n = len(p)
+    in_tree = np.zeros(n, dtype=bool)
+    min_reach = np.full(n, np.inf)
+    source = np.ones(n, dtype=np.int64)
+    src, dst, w = np.empty(n - 1, np.int64), np.empty(n - 1, np.int64), np.empty(n - 1)
+    cur = 0
+    for i in range(n - 1):
+        in_tree[cur] = True
+        d = np.sqrt((p[cur, 0] - p[:, 0]) ** 2 + (p[cur, 1] - p[:, 1]) ** 2)
+        mrd = np.maximum(np.maximum(core[cur], core), d)
+        upd = (mrd < min_reach) & ~in_tree
+        min_reach[upd] = mrd[upd]
+        source[upd] = cur
+        cand = np.where(in_tree, np.inf, min_reach)
+        new = int(np.argmin(cand))               # first minimal index, like the ascending strict-'<' scan
+        src[i], dst[i], w[i] = source[new], new, cand[new]
+        cur = new
+    return src, dst, w
+
+
+def hdbscan_tree_labels_ref(src, dst, w, n, min_cluster_size):
+    """Edges sorted by weight -> labels (-1 noise).  Pure-Python port for small n."""
+    m = n - 1
+    parent = np.full(2 * n - 1, -1, dtype=np.int64)
+    size = np.ones(2 * n - 1, dtype=np.int64)
+    left, right, csize = np.empty(m, np.int64), np.empty(m, np.int64), np.empty(m, np.int64)
+
+    def find(x):
+        r = x
+        while parent[r] != -1:
+            r = parent[r]
+        while parent[x] != -1 and parent[x] != r:
+            parent[x], x = r, parent[x]
+        return r
+    for i in range(m):
+        a, b = find(int(src[i])), find(int(dst[i]))
+        left[i], right[i], csize[i] = a, b, size[a] + size[b]
+        parent[a] = parent[b] = n + i
+        size[n + i] = csize[i]
+
+    def bfs(start):
+        out = [start]
+        h = 0
+        while h < len(out):
+            x = out[h]
+            h += 1
+            if x >= n:
+                out += [int(left[x - n]), int(right[x - n])]
+        return out
+    root = 2 * m
+    relabel = {root: n}
+    ignore = set()
+    rows, nxt = [], n + 1
+    for node in bfs(root):
+        if node in ignore or node < n:
+            continue
+        l, r, dist = int(left[node - n]), int(right[node - n]), w[node - n]
+        lam = 1.0 / dist if dist > 0 else np.inf
+        lc = csize[l - n] if l >= n else 1
+        rc = csize[r - n] if r >= n else 1
+
+        def spill(frm):
+            for x in bfs(frm):
+                if x < n:
+                    rows.append((relabel[node], x, lam, 1))
+                ignore.add(x)
+        if lc >= min_cluster_size and rc >= min_cluster_size:
+            relabel[l] = nxt
+            rows.append((relabel[node], nxt, lam, lc))
+            relabel[r] = nxt + 1
+            rows.append((relabel[node], nxt + 1, lam, rc))
+            nxt += 2
+        elif lc < min_cluster_size and rc < min_cluster_size:
+            spill(l)
+            spill(r)
+        elif lc < min_cluster_size:
+            relabel[r] = relabel[node]
+            spill(l)
+        else:
+            relabel[l] = relabel[node]
+            spill(r)
+    nc = nxt - n
+    birth, stab = np.zeros(nc), np.zeros(nc)
+    for p_, c, lam, s in rows:
+        if c >= n:
+            birth[c - n] = lam
+    for p_, c, lam, s in rows:
+        stab[p_ - n] += (lam - birth[p_ - n]) * s
+    kids = [[] for _ in range(nc)]
+    for p_, c, lam, s in rows:
+        if s > 1:
+            kids[p_ - n].append(c - n)
+    is_cluster = np.ones(nc, dtype=bool)
+    is_cluster[0] = False
+    for c in range(nc - 1, 0, -1):
+        sub = sum(stab[k] for k in kids[c]) if kids[c] else 0.0
+        if sub > stab[c]:
+            is_cluster[c] = False
+            stab[c] = sub
+        else:
+            q = list(kids[c])
+            while q:
+                x = q.pop()
+                is_cluster[x] = False
+                q += kids[x]
+    label_of = np.cumsum(is_cluster) - 1
+    up = {}
+
+    def top(x):
+        while x in up:
+            x = up[x]
+        return x
+    for p_, c, lam, s in rows:      # child rows hang under their parent unless the child is a selected cluster
+        if not (c >= n and is_cluster[c - n]):
+            up[c] = p_
+    labels = np.empty(n, dtype=np.int64)
+    for i in range(n):
+        c = top(i)
+        labels[i] = label_of[c - n] if c != n else -1
+    return labels
+
+
+def hdbscan_ref(points, min_cluster_size):
+    pts = np.asarray(points)
+    core = core_distances_ref(pts, min_cluster_size)
+    src, dst, w = prim_mst_ref(pts, core)
+    order = np.argsort(w)
+    return hdbscan_tree_labels_ref(src[order], dst[order], w[order], len(pts), min_cluster_size)
+
+
+def group_hdbscan_ref(cluster_coords, npoint_thr, not_assigned_label, start_num_preds):
+    labels = hdbscan_ref(cluster_coords, npoint_thr)
+    nums, cnt = np.unique(labels, return_counts=True)
+    valid = nums[(cnt >= npoint_thr) & (nums != -1)]
+    ind = np.isin(labels, valid)
+    out = np.full(len(labels), not_assigned_label, dtype=np.int64)
+    if ind.any():
+        out[ind] = make_labels_consecutive_ref(labels[ind], start_num_preds)
+    return out

@@ -37,11 +37,15 @@ def import_reference():
     # this repo ships a drop-in package also called `tree_learn`; make sure the REFERENCE one wins here
     for k in [k for k in sys.modules if k == 'tree_learn' or k.startswith('tree_learn.')]:
         del sys.modules[k]
-    sys.path.insert(0, REF)
+    # (the reference's `tree_learn` has no __init__.py: a regular package of the same name anywhere on sys.path would
+    # shadow it, so path entries holding this repo's drop-in package are hidden while the reference is imported)
+    saved = list(sys.path)
+    sys.path[:] = [REF] + [p for p in saved if not os.path.isfile(os.path.join(p or '.', 'tree_learn', '__init__.py'))]
     torch.Tensor.cuda = lambda self, *a, **k: self     # cuda_cast (util/train.py:28-43) on a CPU box
     import tree_learn.model as ref_model
     import tree_learn.util.pipeline as ref_pipeline
     import tree_learn.util.train as ref_train
+    sys.path[:] = [REF] + saved
     assert ref_model.__file__.startswith(REF), ref_model.__file__
     return ref_model, ref_pipeline, ref_train
 

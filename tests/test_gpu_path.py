@@ -228,9 +228,6 @@ def test_get_instances_and_knn_match_reference_golden():
     tm = inst != 0
     assigned = pipeline.assign_remaining_points_nearest_neighbor(coords[tm] + offs[tm], inst[tm], -1)
     assert np.array_equal(assigned, g['assigned'])
-    cfg.use_hdbscan = True
-    with pytest.raises(NotImplementedError):
-        pipeline.get_instances(coords, offs, logits, cfg, vert, 0, 0, -1, 1)
 
 
 def test_group_dbscan_label_ids_match_sklearn_golden():

@@ -55,6 +55,10 @@ SIGNATURES = {
     'tl_cluster_radius_cc': (C.c_int, [_P, _I64, _D, _I64, _I64, _I64, _P, _I64P, _P, _SZ, _P]),
     'tl_knn_workspace_bytes': (_SZ, [_I64, _I64]),
     'tl_knn_vote': (C.c_int, [_P, _P, _I64, _P, _I64, _I32, _P, _P, _SZ, _P]),
+    'tl_hdbscan_workspace_bytes': (_SZ, [_I64]),
+    'tl_core_distance': (C.c_int, [_P, _I64, _I32, _P, _P, _SZ, _P]),
+    'tl_mst_prim': (C.c_int, [_P, _P, _I64, _P, _P, _P, _P, _SZ, _P]),
+    'tl_hdbscan_tree_labels': (C.c_int, [_P, _P, _P, _I64, _I64, _P]),
     'tl_bn_stats': (C.c_int, [_P, _I64, _I32, _P, _P]),
     'tl_bn_finalize': (C.c_int, [_P, _I64, _I32, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P]),
     'tl_bn_relu_apply': (C.c_int, [_P, _I64, _I32, _P, _P, _P, _P]),

@@ -5,6 +5,9 @@
 // sklearn's KD-tree evaluates its reduced distance (sum of squares in axis order).
 #include <cub/cub.cuh>
 
+#include <algorithm>
+#include <vector>
+
 #include "tl_common.cuh"
 
 namespace tl {
@@ -236,10 +239,15 @@ __global__ void k_cc_link(const uint64_t* __restrict__ skeys, const int* __restr
 
 __global__ void k_cc_roots(int* parent, int64_t n, int* __restrict__ root, int* __restrict__ size) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int r = uf_find(parent, (int)i);
-    root[i] = r;
-    atomicAdd(&size[r], 1);
+    const bool live = i < n;
+    const int r = live ? uf_find(parent, (int)i) : -1;
+    if (live) root[i] = r;
+    // component sizes: lanes with the same root add once (a few huge components otherwise serialise on one address)
+    const unsigned alive = __ballot_sync(0xffffffffu, live);
+    if (live) {
+        const unsigned peers = __match_any_sync(alive, r);
+        if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&size[r], __popc(peers));
+    }
 }
 
 __global__ void k_cc_valid(const int* __restrict__ root, const int* __restrict__ size, int64_t n, int min_size,
@@ -424,6 +432,166 @@ __global__ void __launch_bounds__(128) k_knn_vote(const float* __restrict__ quer
     out[q] = top.vote(ref_labels);
 }
 
+// ------------------------------------------------------------------------------------------------
+// HDBSCAN (sklearn.cluster.HDBSCAN(min_cluster_size = m), the reference's default clusterer:
+// tree_learn/util/pipeline.py:184-191).  sklearn 1.5-1.9 runs, for Euclidean input:
+//   core distance = distance to the min_samples-th nearest neighbour, the point itself included (KD-tree query),
+//   MST of the mutual-reachability graph max(core_a, core_b, d_ab) by Prim's algorithm over the data matrix
+//   (O(n^2), started at node 0, strict '<' updates, first minimal index wins),
+//   edges sorted by weight -> single-linkage dendrogram -> condensed tree -> stability -> excess-of-mass selection.
+// Here: core distances by a cell-grid search, Prim as one persistent kernel (every step = a parallel relaxation +
+// lexicographic (value, index) argmin + one grid barrier), both in fp64 without FMA contraction like the rest of this file;
+// the dendrogram / condensed-tree pass (O(n), pointer chasing) runs on the host inside this library.
+// ------------------------------------------------------------------------------------------------
+constexpr int kCoreMaxK = 128;
+
+static inline double __longlong_as_double_host(long long v) {
+    double d;
+    memcpy(&d, &v, sizeof(d));
+    return d;
+}
+__global__ void k_fill_f64(double* p, double v, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+__global__ void k_fill_i32b(int* p, int v, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+__global__ void __launch_bounds__(128) k_core_dist(const uint64_t* __restrict__ skeys, const int* __restrict__ sidx,
+                                                   const float* __restrict__ spts, const int* __restrict__ seg_start,
+                                                   const uint64_t* __restrict__ tkeys, const int* __restrict__ tvals,
+                                                   uint64_t mask, int64_t n, int k, double cell, int max_ring,
+                                                   double* __restrict__ core) {
+    int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const double x = spts[j * 2], y = spts[j * 2 + 1];
+    const uint64_t key = skeys[j];
+    const int64_t cx = (int64_t)(key >> (2 * kAxisBits)) - kAxisBias;
+    const int64_t cy = (int64_t)((key >> kAxisBits) & ((1u << kAxisBits) - 1)) - kAxisBias;
+    double top[kCoreMaxK];   // k smallest squared distances, ascending (local memory)
+    for (int t = 0; t < k; ++t) top[t] = 1e300;
+    auto push = [&](double d2) {
+        if (d2 >= top[k - 1]) return;
+        int t = k - 1;
+        while (t > 0 && top[t - 1] > d2) top[t] = top[t - 1], --t;
+        top[t] = d2;
+    };
+    bool done = false;
+    for (int ring = 0; ring <= max_ring && !done; ++ring) {
+        for (int dx = -ring; dx <= ring; ++dx) {
+            const bool edge = (dx == -ring || dx == ring);
+            for (int dy = -ring; dy <= ring; dy += (edge || ring == 0) ? 1 : 2 * ring) {   // shell cells only
+                const int seg = hash_find(tkeys, tvals, mask, cell_key3(cx + dx, cy + dy, 0));
+                if (seg < 0) continue;
+                for (int j2 = seg_start[seg]; j2 < seg_start[seg + 1]; ++j2) {
+                    const double ax = x - (double)spts[j2 * 2], ay = y - (double)spts[j2 * 2 + 1];
+                    push(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)));
+                }
+            }
+        }
+        const double safe = (double)ring * cell;   // every point closer than ring*cell has been seen
+        done = ring > 0 && top[k - 1] <= safe * safe;
+    }
+    if (!done) {   // sparse neighbourhood: exact scan of all points
+        for (int t = 0; t < k; ++t) top[t] = 1e300;
+        for (int64_t j2 = 0; j2 < n; ++j2) {
+            const double ax = x - (double)spts[j2 * 2], ay = y - (double)spts[j2 * 2 + 1];
+            push(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)));
+        }
+    }
+    core[sidx[j]] = __dsqrt_rn(top[k - 1]);
+}
+
+// all CTAs of the (co-resident, cooperatively launched) grid meet; `target` = number of arrivals expected so far
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        while (*(volatile unsigned*)counter < target) {
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+struct PrimBest {
+    double v;
+    int j;
+};
+__device__ __forceinline__ PrimBest prim_min(PrimBest a, PrimBest b) {   // lexicographic (value, index)
+    return (b.v < a.v || (b.v == a.v && b.j < a.j)) ? b : a;
+}
+__device__ __forceinline__ PrimBest prim_block_min(PrimBest b, PrimBest* sh) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        PrimBest o;
+        o.v = __shfl_down_sync(0xffffffffu, b.v, off);
+        o.j = __shfl_down_sync(0xffffffffu, b.j, off);
+        b = prim_min(b, o);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    if (lane == 0) sh[warp] = b;
+    __syncthreads();
+    if (warp == 0) {
+        b = lane < nw ? sh[lane] : PrimBest{1.7976931348623157e308, 0x7fffffff};
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            PrimBest o;
+            o.v = __shfl_down_sync(0xffffffffu, b.v, off);
+            o.j = __shfl_down_sync(0xffffffffu, b.j, off);
+            b = prim_min(b, o);
+        }
+        if (lane == 0) sh[0] = b;
+    }
+    __syncthreads();
+    b = sh[0];
+    __syncthreads();
+    return b;
+}
+
+__global__ void __launch_bounds__(512) k_prim(const float* __restrict__ pts, const double* __restrict__ core, int n,
+                                              double* min_reach, int* source, unsigned char* in_tree, double* blk_v,
+                                              int* blk_j, unsigned* counter, int* __restrict__ mst_src,
+                                              int* __restrict__ mst_dst, double* __restrict__ mst_w) {
+    __shared__ PrimBest sh[32];
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
+    int cur = 0, par = 0;
+    for (int step = 0; step < n - 1; ++step) {
+        const double cx = pts[2 * cur], cy = pts[2 * cur + 1], cc = core[cur];
+        PrimBest best{1.7976931348623157e308, 0x7fffffff};
+        for (int j = gtid; j < n; j += gsize) {
+            if (j == cur) {
+                in_tree[j] = 1;
+                continue;
+            }
+            if (in_tree[j]) continue;
+            const double ax = cx - (double)pts[2 * j], ay = cy - (double)pts[2 * j + 1];
+            const double d = __dsqrt_rn(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)));
+            const double mrd = fmax(fmax(cc, core[j]), d);
+            double mr = min_reach[j];
+            if (mrd < mr) {
+                mr = mrd;
+                min_reach[j] = mrd;
+                source[j] = cur;
+            }
+            best = prim_min(best, PrimBest{mr, j});
+        }
+        best = prim_block_min(best, sh);
+        if (threadIdx.x == 0) blk_v[par * gridDim.x + blockIdx.x] = best.v, blk_j[par * gridDim.x + blockIdx.x] = best.j;
+        grid_barrier(counter, (unsigned)(step + 1) * gridDim.x);
+        PrimBest b{1.7976931348623157e308, 0x7fffffff};
+        for (int t = threadIdx.x; t < (int)gridDim.x; t += blockDim.x)
+            b = prim_min(b, PrimBest{__ldcg(&blk_v[par * gridDim.x + t]), __ldcg(&blk_j[par * gridDim.x + t])});
+        b = prim_block_min(b, sh);
+        if (gtid == 0) mst_src[step] = __ldcg(&source[b.j]), mst_dst[step] = b.j, mst_w[step] = b.v;
+        cur = b.j;
+        par ^= 1;
+    }
+}
+
 }  // namespace tl
 
 using namespace tl;
@@ -575,6 +743,207 @@ int tl_knn_vote(const float* ref_xyz, const int64_t* ref_labels, int64_t n_ref, 
     }
     k_knn_vote<<<(unsigned)((n_query + 127) / 128), 128, 0, stream>>>(query_xyz, n_query, g, ref_labels, k, out_labels);
     TL_LAUNCH_CHECK();
+    return TL_OK;
+}
+
+// ---- HDBSCAN ----------------------------------------------------------------------------------
+size_t tl_hdbscan_workspace_bytes(int64_t n) {
+    if (n <= 0) return 256;
+    return grid_bytes(n) + align_up(n * 8) + align_up(n * 4) + align_up(n) + 2 * align_up(2 * 4096 * 8) + 4096;
+}
+
+int tl_core_distance(const float* points_xy, int64_t n, int32_t k, double* core, void* workspace, size_t workspace_bytes,
+                     void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n == 0) return TL_OK;
+    TL_REQUIRE(k >= 1 && k <= kCoreMaxK && k <= n, "tl_core_distance: k=%d must be in [1, min(%d, n=%lld)]", k, kCoreMaxK,
+               (long long)n);
+    TL_REQUIRE(n < (1ll << 31), "tl_core_distance: n=%lld too large", (long long)n);
+    Carver c(workspace, workspace_bytes);
+    CellGrid g;
+    TL_REQUIRE(carve_grid(c, n, g), "tl_core_distance: workspace too small");
+    const double cell = 0.5;
+    int rc = build_grid<2>(points_xy, n, cell, g, stream);
+    if (rc != TL_OK) return rc;
+    k_core_dist<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(g.keys_out, g.idx_out, g.spts, g.seg_start, g.tkeys, g.tvals,
+                                                                g.cap - 1, n, k, cell, 6, core);
+    TL_LAUNCH_CHECK();
+    return TL_OK;
+}
+
+int tl_mst_prim(const float* points_xy, const double* core, int64_t n, int32_t* mst_src, int32_t* mst_dst, double* mst_w,
+                void* workspace, size_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n <= 1) return TL_OK;
+    TL_REQUIRE(n < (1ll << 31), "tl_mst_prim: n=%lld too large", (long long)n);
+    int dev = 0, sms = 0, coop = 0;
+    TL_CUDA_CHECK(cudaGetDevice(&dev));
+    TL_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    TL_CUDA_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+    TL_REQUIRE(coop, "tl_mst_prim: device does not support cooperative launches");
+    int grid = sms;                                   // one 512-thread CTA per SM: co-resident by construction
+    if ((int64_t)grid * 512 > n) grid = (int)((n + 511) / 512);
+    Carver c(workspace, workspace_bytes);
+    double* min_reach = c.take<double>(n);
+    int* source = c.take<int>(n);
+    unsigned char* in_tree = c.take<unsigned char>(n);
+    double* blk_v = c.take<double>(2 * 4096);
+    int* blk_j = c.take<int>(2 * 4096);
+    unsigned* counter = c.take<unsigned>(64);
+    TL_REQUIRE(c.ok() && grid <= 4096, "tl_mst_prim: workspace too small");
+    // min_reachability = +inf (0x7ff0...), current_sources = 1, in_tree = 0 (sklearn _linkage.pyx initial state)
+    TL_CUDA_CHECK(cudaMemsetAsync(in_tree, 0, n, stream));
+    TL_CUDA_CHECK(cudaMemsetAsync(counter, 0, 64 * sizeof(unsigned), stream));
+    k_fill_f64<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(min_reach, __longlong_as_double_host(0x7ff0000000000000ll), n);
+    TL_LAUNCH_CHECK();
+    k_fill_i32b<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(source, 1, n);
+    TL_LAUNCH_CHECK();
+    int n32 = (int)n;
+    void* args[] = {(void*)&points_xy, (void*)&core, (void*)&n32, (void*)&min_reach, (void*)&source, (void*)&in_tree,
+                    (void*)&blk_v, (void*)&blk_j, (void*)&counter, (void*)&mst_src, (void*)&mst_dst, (void*)&mst_w};
+    TL_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_prim, dim3(grid), dim3(512), args, 0, stream));
+    count_launch();
+    return TL_OK;
+}
+
+// Host pass: edges (already ordered by weight: the caller applies numpy's argsort so that ties break like sklearn's
+// `_process_mst`) -> single-linkage dendrogram -> condensed tree -> stability -> EOM selection -> labels (-1 = noise).
+// Restates sklearn/cluster/_hdbscan/_linkage.pyx::make_single_linkage and _tree.pyx::{_condense_tree, _compute_stability,
+// _get_clusters (eom, allow_single_cluster=False, epsilon=0, no max size), _do_labelling}; traversal orders are kept
+// because they fix both the floating-point summation order of the stabilities and the numbering of the clusters.
+int tl_hdbscan_tree_labels(const int64_t* src, const int64_t* dst, const double* w, int64_t n, int64_t min_cluster_size,
+                           int64_t* labels) {
+    TL_REQUIRE(n >= 2 && src && dst && w && labels && min_cluster_size >= 2, "tl_hdbscan_tree_labels: bad arguments");
+    const int64_t m = n - 1, root = 2 * m;
+    // ---- single linkage (scipy hierarchy format; node n + i = merge i)
+    std::vector<int64_t> parent(2 * n - 1, -1), usize(2 * n - 1, 0), left(m), right(m), csize(m);
+    for (int64_t i = 0; i < n; ++i) usize[i] = 1;
+    int64_t next_label = n;
+    auto fast_find = [&](int64_t x) {
+        int64_t p = x;
+        while (parent[x] != -1) x = parent[x];
+        while (parent[p] != x && parent[p] != -1) {   // path compression
+            const int64_t q = parent[p];
+            parent[p] = x;
+            p = q;
+        }
+        return x;
+    };
+    for (int64_t i = 0; i < m; ++i) {
+        const int64_t a = fast_find(src[i]), b = fast_find(dst[i]);
+        TL_REQUIRE(a != b, "tl_hdbscan_tree_labels: edge %lld does not join two components (input is not a spanning tree)",
+                   (long long)i);
+        left[i] = a, right[i] = b, csize[i] = usize[a] + usize[b];
+        parent[a] = next_label, parent[b] = next_label, usize[next_label] = csize[i];
+        ++next_label;
+    }
+    // ---- condensed tree
+    struct Row {
+        int64_t parent, child;
+        double lambda;
+        int64_t size;
+    };
+    std::vector<Row> rows;
+    rows.reserve(2 * n);
+    auto bfs = [&](int64_t start, std::vector<int64_t>& out) {   // level order, children as (left, right)
+        out.clear();
+        out.push_back(start);
+        for (size_t h = 0; h < out.size(); ++h) {
+            const int64_t x = out[h];
+            if (x >= n) out.push_back(left[x - n]), out.push_back(right[x - n]);
+        }
+    };
+    std::vector<int64_t> order, sub;
+    bfs(root, order);
+    std::vector<int64_t> relabel(root + 1, 0);
+    std::vector<char> ignore(root + 1, 0);
+    relabel[root] = n;
+    int64_t next_cluster = n + 1;
+    auto spill = [&](int64_t node, int64_t from, double lam) {   // every point below `from` leaves cluster `node` at lam
+        bfs(from, sub);
+        for (int64_t x : sub) {
+            if (x < n) rows.push_back(Row{relabel[node], x, lam, 1});
+            ignore[x] = 1;
+        }
+    };
+    for (int64_t node : order) {
+        if (ignore[node] || node < n) continue;
+        const int64_t l = left[node - n], r = right[node - n];
+        const double dist = w[node - n];
+        const double lam = dist > 0.0 ? 1.0 / dist : __longlong_as_double_host(0x7ff0000000000000ll);
+        const int64_t lc = l >= n ? csize[l - n] : 1, rc = r >= n ? csize[r - n] : 1;
+        if (lc >= min_cluster_size && rc >= min_cluster_size) {
+            relabel[l] = next_cluster++;
+            rows.push_back(Row{relabel[node], relabel[l], lam, lc});
+            relabel[r] = next_cluster++;
+            rows.push_back(Row{relabel[node], relabel[r], lam, rc});
+        } else if (lc < min_cluster_size && rc < min_cluster_size) {
+            spill(node, l, lam);
+            spill(node, r, lam);
+        } else if (lc < min_cluster_size) {
+            relabel[r] = relabel[node];
+            spill(node, l, lam);
+        } else {
+            relabel[l] = relabel[node];
+            spill(node, r, lam);
+        }
+    }
+    // ---- stability (cluster ids n .. next_cluster-1; the root cluster n is born at lambda 0)
+    const int64_t n_clusters = next_cluster - n;
+    std::vector<double> birth(n_clusters, 0.0), stab(n_clusters, 0.0);
+    for (const Row& rw : rows)
+        if (rw.child >= n) birth[rw.child - n] = rw.lambda;
+    birth[0] = 0.0;
+    for (const Row& rw : rows) stab[rw.parent - n] += (rw.lambda - birth[rw.parent - n]) * (double)rw.size;
+    // ---- excess of mass over the cluster tree (children of a cluster: the two rows with size > 1, in row order)
+    std::vector<std::vector<int64_t>> kids(n_clusters);
+    for (const Row& rw : rows)
+        if (rw.size > 1) kids[rw.parent - n].push_back(rw.child - n);
+    std::vector<char> is_cluster(n_clusters, 1);
+    is_cluster[0] = 0;   // allow_single_cluster = False: the root is never selected
+    for (int64_t c = n_clusters - 1; c >= 1; --c) {
+        double subtree = 0.0;
+        for (int64_t k : kids[c]) subtree += stab[k];
+        if (subtree > stab[c]) {
+            is_cluster[c] = 0;
+            stab[c] = subtree;
+        } else {   // keep c: nothing below it is a cluster
+            std::vector<int64_t> q(kids[c].begin(), kids[c].end());
+            for (size_t h = 0; h < q.size(); ++h) {
+                is_cluster[q[h]] = 0;
+                for (int64_t k : kids[q[h]]) q.push_back(k);
+            }
+        }
+    }
+    std::vector<int64_t> label_of(n_clusters, -1);
+    int64_t next = 0;
+    for (int64_t c = 0; c < n_clusters; ++c)
+        if (is_cluster[c]) label_of[c] = next++;
+    // ---- labelling: union every row whose child is not a selected cluster; a point takes the label of the top-most
+    // cluster of its set (sklearn's TreeUnionFind with union by rank yields exactly that representative)
+    std::vector<int64_t> up(n + n_clusters), rank(n + n_clusters, 0);
+    for (int64_t i = 0; i < n + n_clusters; ++i) up[i] = i;
+    auto find = [&](int64_t x) {
+        int64_t r = x;
+        while (up[r] != r) r = up[r];
+        while (up[x] != r) {
+            const int64_t q = up[x];
+            up[x] = r;
+            x = q;
+        }
+        return r;
+    };
+    for (const Row& rw : rows) {
+        if (rw.child >= n && is_cluster[rw.child - n]) continue;
+        const int64_t xr = find(rw.parent), yr = find(rw.child);
+        if (rank[xr] < rank[yr]) up[xr] = yr;
+        else if (rank[xr] > rank[yr]) up[yr] = xr;
+        else up[yr] = xr, ++rank[xr];
+    }
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t c = find(i);
+        labels[i] = (c >= n && c != n) ? label_of[c - n] : -1;
+    }
     return TL_OK;
 }
 

@@ -143,10 +143,52 @@ def group_dbscan(cluster_coords, radius, npoint_thr, not_assigned_label_in_group
     return labels.cpu().numpy()
 
 
+def hdbscan_cuda(points_xy, min_cluster_size):
+    """sklearn.cluster.HDBSCAN(min_cluster_size).fit_predict on [n,2] f32 CUDA points -> numpy int64 labels (-1 noise).
+    Core distances and the Prim MST of the mutual-reachability graph run on the GPU (tl_core_distance, tl_mst_prim);
+    the edges are ordered with numpy's argsort exactly like sklearn's `_process_mst`, and the O(n) dendrogram /
+    condensed-tree / excess-of-mass pass runs in the library's host code (tl_hdbscan_tree_labels)."""
+    lib = _lib.load()
+    n = int(points_xy.shape[0])
+    if n == 1:
+        raise ValueError('n_samples=1 while HDBSCAN requires more than one sample')
+    if min_cluster_size > n:
+        raise ValueError(f'min_samples ({min_cluster_size}) must be at most the number of samples in X ({n})')
+    dev = points_xy.device
+    pts = points_xy.contiguous().float()
+    core = torch.empty(n, dtype=torch.float64, device=dev)
+    src = torch.empty(n - 1, dtype=torch.int32, device=dev)
+    dst = torch.empty(n - 1, dtype=torch.int32, device=dev)
+    w = torch.empty(n - 1, dtype=torch.float64, device=dev)
+    wsb = lib.tl_hdbscan_workspace_bytes(n)
+    ws = _ws(wsb, dev)
+    check(lib.tl_core_distance(ptr(pts), n, int(min_cluster_size), ptr(core), ptr(ws), wsb, stream_ptr()))
+    check(lib.tl_mst_prim(ptr(pts), ptr(core), n, ptr(src), ptr(dst), ptr(w), ptr(ws), wsb, stream_ptr()))
+    w_h = w.cpu().numpy()
+    order = np.argsort(w_h)                      # sklearn: np.argsort(min_spanning_tree["distance"])
+    src_h = np.ascontiguousarray(src.cpu().numpy().astype(np.int64)[order])
+    dst_h = np.ascontiguousarray(dst.cpu().numpy().astype(np.int64)[order])
+    w_h = np.ascontiguousarray(w_h[order])
+    labels = np.empty(n, dtype=np.int64)
+    check(lib.tl_hdbscan_tree_labels(src_h.ctypes.data, dst_h.ctypes.data, w_h.ctypes.data, n, int(min_cluster_size),
+                                     labels.ctypes.data))
+    return labels
+
+
 def group_hdbscan(cluster_coords, npoint_thr, not_assigned_label_in_grouping, start_num_preds):
-    raise NotImplementedError(
-        'treelearn_b200: GPU HDBSCAN (SURVEY.md §8 f1) is not built yet and there is no CPU fallback; '
-        'set grouping.use_hdbscan: False to use the DBSCAN-equivalent GPU clustering')
+    """HDBSCAN(min_cluster_size=npoint_thr) + size filter + consecutive relabel (reference util/pipeline.py:184-191)."""
+    dev = _dev()
+    if len(cluster_coords) == 0:
+        return np.zeros(0, dtype=np.int64)
+    pts = torch.from_numpy(np.ascontiguousarray(cluster_coords[:, :2], dtype=np.float32)).to(dev)
+    labels = hdbscan_cuda(pts, npoint_thr)
+    cluster_nums, n_points = np.unique(labels, return_counts=True)
+    valid = cluster_nums[(n_points >= npoint_thr) & (cluster_nums != -1)]
+    ind_valid = np.isin(labels, valid)
+    out = np.full(len(labels), not_assigned_label_in_grouping, dtype=np.int64)
+    if ind_valid.any():
+        out[ind_valid], _ = make_labels_consecutive(labels[ind_valid], start_num=start_num_preds)
+    return out
 
 
 def get_instances(coords, offset, semantic_prediction_logits, grouping_cfg, verticality_feat, tree_class_in_dataset,
@@ -204,16 +246,19 @@ def instances_cuda(coords, offsets, logits, verticality, grouping_cfg, tree_clas
                    not_assigned_label=-1, start_num_preds=1, n_neighbors=5):
     """Device-resident `get_instances` (DBSCAN branch) + `assign_remaining_points_nearest_neighbor` exactly as
     tools/pipeline/pipeline.py:89-94 chains them; all inputs CUDA tensors, returns (labels [P] i64 CUDA, n_clusters)."""
-    if grouping_cfg.use_hdbscan:
-        group_hdbscan(None, None, None, None)
     shifted = coords + offsets
     tree_mask = logits.float().softmax(dim=-1)[:, tree_class] >= grouping_cfg.tree_conf_thresh
     mask = tree_mask & (verticality > grouping_cfg.tau_vert) & (offsets[:, 2].abs() < grouping_cfg.tau_off)
     ind = mask.nonzero().squeeze(1)
     pred = torch.full((coords.shape[0],), non_trees_label, dtype=torch.int64, device=coords.device)
     pred[tree_mask] = not_assigned_label
-    lab, n_clusters = group_dbscan_cuda(shifted[ind][:, :2], grouping_cfg.tau_group, grouping_cfg.tau_min,
-                                        not_assigned_label, start_num_preds)
+    if grouping_cfg.use_hdbscan:
+        lab = torch.from_numpy(group_hdbscan(shifted[ind][:, :2].cpu().numpy(), grouping_cfg.tau_min, not_assigned_label,
+                                             start_num_preds)).to(coords.device)
+        n_clusters = int(lab.max().item()) - start_num_preds + 1 if (lab != not_assigned_label).any() else 0
+    else:
+        lab, n_clusters = group_dbscan_cuda(shifted[ind][:, :2], grouping_cfg.tau_group, grouping_cfg.tau_min,
+                                            not_assigned_label, start_num_preds)
     pred[ind] = lab
     tree_idx = (pred != non_trees_label).nonzero().squeeze(1)
     tp = pred[tree_idx]
