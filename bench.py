@@ -32,6 +32,17 @@ MODEL_CFG = dict(channels=32, num_blocks=7, use_feats=False, use_coords=False, s
 METRIC = 'Mvoxels/s sparse U-Net fwd (+cluster) per tile'
 
 
+def conv_traffic(workload, mode):
+    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of all k_conv_tc launches of one forward, from the
+    committed ncu capture of the same workload / mode (profiles/r01_conv_traffic.json, written by
+    tools/summarise_conv_traffic.py); None when no capture matches."""
+    path = os.path.join(ROOT, 'profiles', 'r01_conv_traffic.json')
+    if not os.path.exists(path):
+        return None
+    t = json.load(open(path))
+    return t.get('dram_bytes_per_step') if (t.get('workload'), t.get('mode')) == (workload, mode) else None
+
+
 def peaks():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
@@ -167,7 +178,7 @@ def run_b200(args):
     roofline = {'bound': 'hbm', 'kernel': 'k_conv_simt (segmented gather-GEMM sparse conv)' if args.mode == 'fp32'
                 else f'k_conv_tc (tcgen05 {args.mode} gather-GEMM sparse conv)',
                 'achieved': round(achieved, 1), 'peak': peak, 'unit': 'GB/s', 'frac': round(achieved / peak, 4),
-                'traffic': None, 'peak_source': peak_src, 'launches_per_step': per_step,
+                'traffic': conv_traffic(args.workload, args.mode), 'peak_source': peak_src, 'launches_per_step': per_step,
                 'kernel_ms_per_step': round(conv_ms / args.steps, 3),
                 'kernel_share_of_step': round(conv_ms / args.steps / ms_res, 3),
                 'alg_bytes_per_step': int(conv_bytes / args.steps),

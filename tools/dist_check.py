@@ -37,12 +37,6 @@ torch.manual_seed(0)
 net = synth.randomize_bn_stats(TreeLearn(use_feats=False, use_coords=False, spatial_shape=[500, 500, 1000], mode='f16')).cuda().eval()
 coords, labels, ncl = tdist.segment_plot(net, tiles, G)
 torch.cuda.synchronize()
-if world > 1:
-    ref = [None]
-    if rank == 0:
-        pass
-    # every rank recomputes the single-rank answer locally (group=None path without sharding)
-    saved = dist.group.WORLD
 rows_local = coords.shape[0]
 sig = torch.tensor([rows_local, int(ncl), int(labels.sum()), int((labels > 0).sum())], device='cuda', dtype=torch.int64)
 if world > 1:
@@ -51,7 +45,6 @@ if world > 1:
     assert all(torch.equal(s, sigs[0]) for s in sigs), [s.tolist() for s in sigs]
 # single-process reference: run all tiles here and compare (cheap: 9 small tiles)
 import treelearn_b200.dist as tdist_mod  # noqa: E402
-orig = (dist.is_initialized, )
 dist_is_init = dist.is_initialized
 try:
     dist.is_initialized = lambda: False          # makes segment_plot / allgather_rows take the single-rank path
@@ -65,7 +58,7 @@ if rank == 0:
 # ---- 2. data-parallel training step ------------------------------------------------------------------------------
 def make_net():
     torch.manual_seed(1)
-    return TreeLearn(channels=32, num_blocks=3, use_feats=False, use_coords=False, spatial_shape=[500, 500, 1000], mode='tf32').cuda()
+    return TreeLearn(channels=32, num_blocks=3, use_feats=False, use_coords=False, spatial_shape=[500, 500, 1000], mode='fp32').cuda()
 
 batches = [synth.make_batch([synth.synth_forest(edge=6.0, n_trees=3, seed=20 + r, ground_density=200.0)], inner_edge=4.0)
            for r in range(world)]
@@ -87,9 +80,11 @@ for p, a in zip(ref.parameters(), acc):
     p.grad = a / world
 ropt.step()
 err = max((p.detach() - q.detach()).abs().max().item() for p, q in zip(net.parameters(), ref.parameters()))
-assert err < 1e-5, err
+step = max((1e-2 * a / world).abs().max().item() for a in acc)       # largest parameter update of this step
+assert err < 1e-3 * step + 1e-7, (err, step)                        # fp32 atomics order only
 if rank == 0:
-    print(f'DP training check ok: world {world}, max |param - reference| after one all-reduced step = {err:.2e}, loss {loss.item():.4f}')
+    print(f'DP training check ok: world {world}, max |param - reference| after one all-reduced step = {err:.2e} '
+          f'(largest update {step:.2e}), loss {loss.item():.4f}')
 if world > 1:
     dist.barrier()
     dist.destroy_process_group()
