@@ -37,7 +37,7 @@ constexpr int kSchedWarp = kProducerWarps + 5;          // 17: builds each work 
 constexpr int kWeightWarp = kProducerWarps + 6;         // 18: one thread bulk-copies (TMA) each chunk's weight slab
 constexpr int kThreads = 32 * (kProducerWarps + 4 + 3);
 constexpr int MAX_CHUNKS = 448;                         // live (segment, offset, k-block) entries per work item
-constexpr int IDX_ROWS = 32;                         // rulebook rows (segment, offset) staged per tile
+constexpr int IDX_ROWS = 28;                         // rulebook rows (segment, offset) staged per tile (3^3 table + spare)
 constexpr int IDX_BUF_BYTES = IDX_ROWS * BM * 4 + MAX_CHUNKS * 4 + 64;   // rulebook rows + chunk list + count
 constexpr int NDESC = 3;                             // work-item descriptors in flight: the scheduler runs NDESC-1 items ahead
 constexpr int EPI_BYTES = 4 * 32 * 128;              // per epilogue warp: 32 rows x 32 fp32 columns, transposed for coalescing
@@ -370,10 +370,10 @@ __device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
 // One warp gathers the 128 rows of a chunk: lane (sub, chunk) copies the 16 B piece `chunk` of rows sub, sub + RPI, ...
 // Rulebook entries come from the staged table in batches of 8 (independent shared-memory loads first, copies after).
 // MODE 0: cp.async.cg with zero-fill for absent rows, 1: cp.async.ca with zero-fill, 2: cp.async.cg, absent rows read zeros.
-template <int EB, int MODE>
+template <int ROW, int MODE>
 __device__ __forceinline__ void gather_rows(uint32_t ia, uint32_t dst0, uint32_t a_off_even, uint32_t a_off_odd, uint64_t src0,
                                             uint32_t seg_stride, uint64_t zsrc0, uint32_t zr0) {
-    constexpr int ROW = BK * EB, RPI = 32 / (ROW / 16), NR = BM / RPI, BATCH = 8;
+    constexpr int RPI = 32 / (ROW / 16), NR = BM / RPI, BATCH = 8;
 #pragma unroll
     for (int i0 = 0; i0 < NR; i0 += BATCH) {
         int r[BATCH];
@@ -403,9 +403,11 @@ __device__ __forceinline__ void gather_rows(uint32_t ia, uint32_t dst0, uint32_t
 //   warp  17      scheduler: one work item ahead it stages the item's rulebook rows (cp.async) and the list of live
 //                 (segment, offset, k-block) chunks in shared memory, so nobody else evaluates masks or split ranges
 //   warp  18      weight loader (lane 0): one TMA bulk copy per chunk of the pre-swizzled [C_out x 32] weight slab
-template <int EB>   // bytes per operand element: 4 = fp32 storage / kind::tf32, 2 = fp16 storage / kind::f16
+// EB: bytes per operand element (4 = fp32 storage / kind::tf32, 2 = fp16 storage / kind::f16); BKC: channels per chunk
+// (32, or 64 for fp16 segments whose width is a multiple of 64: 128 B rows = whole cache lines, half the chunks)
+template <int EB, int BKC>
 __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const tl_conv_desc d, const Launch P) {
-    constexpr int ROW = BK * EB;          // bytes per operand row in a stage (one swizzle row)
+    constexpr int ROW = BKC * EB;         // bytes per operand row in a stage (one swizzle row: 64 or 128 B)
     constexpr int CH = ROW / 16;          // 16 B chunks per row
     constexpr int RPI = 32 / CH;          // rows covered by one warp-wide LDGSTS
     constexpr int KSTEPS = ROW / 32;      // UMMA K steps (32 B each) per stage
@@ -440,7 +442,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const tl_conv_desc d, c
         const uint32_t t = L.segtab + 32 * threadIdx.x;
         const uint64_t src = (uint64_t)sg.src, wgt = (uint64_t)sg.weight;
         st_shared_v4(t, (uint32_t)src, (uint32_t)(src >> 32), (uint32_t)wgt, (uint32_t)(wgt >> 32));
-        st_shared_v4(t + 16, (uint32_t)(sg.src_stride * EB), (uint32_t)(sg.c_in / BK),
+        st_shared_v4(t + 16, (uint32_t)(sg.src_stride * EB), (uint32_t)(sg.c_in / BKC),
                      sg.index ? (uint32_t)P.idx_base[threadIdx.x] : 0xffffffffu, 0u);
     }
     if (warp == kMmaWarp) {  // TMEM allocation is owned by the MMA warp
@@ -465,7 +467,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const tl_conv_desc d, c
             int ord = 0, pos = 0;
             for (int s = 0; s < d.n_seg; ++s) {
                 const tl_conv_seg& sg = d.seg[s];
-                const int kblocks = sg.c_in / BK;
+                const int kblocks = sg.c_in / BKC;
                 if (P.prefetch && lane == 0 && (!sg.index || sg.n_off == 27) && sg.src_stride == sg.c_in) {
                     // rows [128 t, 128 t + 128) of the source are this tile's centre taps and most of its 3^3 neighbours
                     // (Morton order): pull them into L2 one work item ahead so the row gathers mostly hit L2
@@ -561,11 +563,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const tl_conv_desc d, c
                     if (seg_idx != 0xffffffffu) {
                         const uint32_t ia = L.idx(buf, (int)(seg_idx + k), sub);
                         if (P.zero_row)
-                            gather_rows<EB, 2>(ia, dst0, a_off_even, a_off_odd, src0, seg_stride, zsrc0, zr0);
+                            gather_rows<ROW, 2>(ia, dst0, a_off_even, a_off_odd, src0, seg_stride, zsrc0, zr0);
                         else if (P.use_cg)
-                            gather_rows<EB, 0>(ia, dst0, a_off_even, a_off_odd, src0, seg_stride, zsrc0, zr0);
+                            gather_rows<ROW, 0>(ia, dst0, a_off_even, a_off_odd, src0, seg_stride, zsrc0, zr0);
                         else
-                            gather_rows<EB, 1>(ia, dst0, a_off_even, a_off_odd, src0, seg_stride, zsrc0, zr0);
+                            gather_rows<ROW, 1>(ia, dst0, a_off_even, a_off_odd, src0, seg_stride, zsrc0, zr0);
                     } else {   // identity segment (1x1 projection / residual input): row = tile row
 #pragma unroll 4
                         for (int i = 0; i < NR; ++i) {
@@ -595,7 +597,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const tl_conv_desc d, c
 #pragma unroll
             for (int s = 0; s < TL_MAX_SEG; ++s) {
                 wbase[s] = s < d.n_seg ? (uint64_t)d.seg[s].weight : 0;
-                wkb[s] = s < d.n_seg ? (uint32_t)(d.seg[s].c_in / BK) : 1u;
+                wkb[s] = s < d.n_seg ? (uint32_t)(d.seg[s].c_in / BKC) : 1u;
             }
             uint32_t slot = 0, phase = 0, witer = 0;
             for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++witer) {
@@ -921,15 +923,24 @@ int conv_fwd_tc(const tl_conv_desc& d, cudaStream_t stream, bool half) {
         }
         return conv_fwd_simt(d, stream);
     }
-    const int row_bytes = half ? 64 : 128;
+    // fp16 convolutions whose every segment is a multiple of 64 channels wide run 64-channel chunks (128 B rows, SWIZZLE_128B);
+    // the weights must be packed with the same rule (sparse.pack_weight_tc)
+    int bkc = 32;
+    if (half && env_int("TL_TC_BK64", 1)) {
+        bkc = 64;
+        for (int s = 0; s < d.n_seg; ++s)
+            if (d.seg[s].c_in % 64 != 0) bkc = 32;
+    }
+    const int row_bytes = half ? 2 * bkc : 128;
     static int num_sms = 0, smem_budget = 0, split_target = 0;
     if (!num_sms) {
         int dev = 0;
         TL_CUDA_CHECK(cudaGetDevice(&dev));
         TL_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-        TL_CUDA_CHECK(cudaFuncSetAttribute(tc::k_conv_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        TL_CUDA_CHECK(cudaFuncSetAttribute(tc::k_conv_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        smem_budget = env_int("TL_TC_SMEM_KB", 212) * 1024;   // keep the rest of the 228 KB as L1 for the gather
+        TL_CUDA_CHECK(cudaFuncSetAttribute(tc::k_conv_tc<4, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        TL_CUDA_CHECK(cudaFuncSetAttribute(tc::k_conv_tc<2, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        TL_CUDA_CHECK(cudaFuncSetAttribute(tc::k_conv_tc<2, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        smem_budget = env_int("TL_TC_SMEM_KB", 200) * 1024;   // keep the rest of the 228 KB as L1 for the gather
         split_target = env_int("TL_TC_SPLIT_WAVES", 1);        // split-K until work items >= waves * SMs
     }
     const int n = d.c_out;
@@ -945,10 +956,22 @@ int conv_fwd_tc(const tl_conv_desc& d, cudaStream_t stream, bool half) {
     // round trip hands over a whole slot, so the single-warp MMA / weight-loader loops pay their fixed cost once per q chunks
     const size_t sub = (size_t)(tc::BM + n) * row_bytes;
     const int ring_budget = smem_budget - 2048 - tc::NDESC * tc::IDX_BUF_BYTES - tc::EPI_BYTES;
-    int q = env_int("TL_TC_Q", 4);
-    if (q > 8) q = 8;
-    while (q & (q - 1)) --q;   // power of two
-    while (q > 1 && (size_t)ring_budget / (q * sub) < 3) q >>= 1;
+    // q = chunks per slot (a divisor of the 12 gather warps): the largest of 4, 3, 2, 1 that still leaves `min_slots` slots.
+    // Measured (profiles/r01_conv_tc_history.md): bigger slots beat more chunks in flight, and a ring that squeezes the L1
+    // below ~25 KB slows the gather down (cp.async misses are tracked in L1), hence the 200 KB default budget.
+    int q = env_int("TL_TC_Q", 0);
+    const int min_slots = env_int("TL_TC_MIN_SLOTS", 3);
+    if (q <= 0 || tc::kProducerWarps % q != 0) {
+        q = 1;
+        const int cand[4] = {4, 3, 2, 1};
+        for (int c = 0; c < 4; ++c)
+            if ((int)((size_t)ring_budget / (cand[c] * sub)) >= min_slots) {
+                q = cand[c];
+                break;
+            }
+    }
+    while (q > 1 && (size_t)ring_budget / (q * sub) < 2) --q;
+    while (tc::kProducerWarps % q != 0) --q;
     int stages = (int)(ring_budget / (q * sub));
     if (stages < 2) stages = 2;
     if (stages > tc::MAX_STAGES) stages = tc::MAX_STAGES;
@@ -968,7 +991,7 @@ int conv_fwd_tc(const tl_conv_desc& d, cudaStream_t stream, bool half) {
     const size_t smem = tc::smem_bytes(n, stages * q, row_bytes);
     P.num_tiles = (d.n_out + tc::BM - 1) / tc::BM;
     P.chunks_total = 0;
-    for (int s = 0; s < d.n_seg; ++s) P.chunks_total += d.seg[s].n_off * (d.seg[s].c_in / tc::BK);
+    for (int s = 0; s < d.n_seg; ++s) P.chunks_total += d.seg[s].n_off * (d.seg[s].c_in / bkc);
     int idx_rows = 0;
     for (int s = 0; s < d.n_seg; ++s) {
         P.idx_base[s] = 0, P.idx_owner[s] = 0;
@@ -1000,8 +1023,9 @@ int conv_fwd_tc(const tl_conv_desc& d, cudaStream_t stream, bool half) {
     }
     int grid = P.num_tiles * P.splits;
     if (grid > num_sms) grid = num_sms;   // 1 CTA per SM (launch bounds); persistent over work items
-    if (half) tc::k_conv_tc<2><<<grid, tc::kThreads, smem, stream>>>(d, P);
-    else tc::k_conv_tc<4><<<grid, tc::kThreads, smem, stream>>>(d, P);
+    if (half && bkc == 64) tc::k_conv_tc<2, 64><<<grid, tc::kThreads, smem, stream>>>(d, P);
+    else if (half) tc::k_conv_tc<2, 32><<<grid, tc::kThreads, smem, stream>>>(d, P);
+    else tc::k_conv_tc<4, 32><<<grid, tc::kThreads, smem, stream>>>(d, P);
     TL_LAUNCH_CHECK();
     if (P.splits > 1) {
         const int64_t total = (int64_t)d.n_out * d.c_out;

@@ -7,6 +7,7 @@ in Morton order (batch-major), so the 2^3 children of a coarse voxel are adjacen
 torch only provides device memory and the stream.
 """
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 from typing import List, Optional
 
@@ -137,21 +138,25 @@ def round_tf32(w):
     return ((i + 0x0FFF + ((i >> 13) & 1)) & ~0x1FFF).view(torch.float32)
 
 
-def pack_weight_tc(w, half):
-    """w [n_off, C_out, C_in] -> the tcgen05 path's B-operand layout [n_off, C_in/32, C_out, 32]: one contiguous
-    [C_out x 32-channel] slab per (offset, k-block) whose rows already carry the UMMA shared-memory swizzle (16 B chunk
-    c of row n sits at c ^ (n & 7) for 128 B fp32/TF32 rows, at c ^ ((n >> 1) & 3) for 64 B fp16 rows), so the kernel
-    lands a slab in its B stage with a single TMA bulk copy.  fp16 when `half`, else fp32 rounded to TF32."""
+def pack_weight_tc(w, half, bk=None):
+    """w [n_off, C_out, C_in] -> the tcgen05 path's B-operand layout [n_off, C_in/bk, C_out, bk]: one contiguous
+    [C_out x bk-channel] slab per (offset, k-block) whose rows already carry the UMMA shared-memory swizzle (16 B chunk
+    c of row n sits at c ^ (n & 7) for 128 B rows, at c ^ ((n >> 1) & 3) for 64 B rows), so the kernel lands a slab in
+    its B stage with a single TMA bulk copy.  fp16 when `half`, else fp32 rounded to TF32.  bk = channels per chunk:
+    32, or 64 for fp16 weights whose C_in is a multiple of 64 (the rule csrc/tl_conv_tc.cu::conv_fwd_tc applies)."""
     k, co, ci = w.shape
     assert ci % 32 == 0 and co % 32 == 0, (ci, co)
+    if bk is None:
+        bk = 64 if (half and ci % 64 == 0 and os.environ.get('TL_TC_BK64', '1') != '0') else 32
     t = w.detach().half() if half else round_tf32(w.detach().float())
-    ch = 4 if half else 8                      # 16 B chunks per 32-channel row
-    t = t.reshape(k, co, ci // 32, ch, 32 // ch).permute(0, 2, 1, 3, 4)      # [k, kb, co, chunk, elems]
+    row_bytes = bk * (2 if half else 4)
+    ch = row_bytes // 16                       # 16 B chunks per row
+    t = t.reshape(k, co, ci // bk, ch, bk // ch).permute(0, 2, 1, 3, 4)      # [k, kb, co, chunk, elems]
     n = torch.arange(co, device=w.device)
-    x = ((n >> 1) & 3) if half else (n & 7)
+    x = (n & 7) if row_bytes == 128 else ((n >> 1) & 3)
     src_chunk = torch.arange(ch, device=w.device)[None, :] ^ x[:, None]     # destination chunk c holds source chunk c ^ x
-    t = torch.gather(t, 3, src_chunk[None, None, :, :, None].expand(k, ci // 32, co, ch, 32 // ch))
-    return t.reshape(k, ci // 32, co, 32).contiguous()
+    t = torch.gather(t, 3, src_chunk[None, None, :, :, None].expand(k, ci // bk, co, ch, bk // ch))
+    return t.reshape(k, ci // bk, co, bk).contiguous()
 
 
 SPLITK_MAX_ROWS = 2 * 148 * TILE_ROWS   # below two waves of 128-row tiles the library may split K over CTAs
