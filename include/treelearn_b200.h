@@ -180,6 +180,11 @@ int tl_bn_relu_apply(const float* x, int64_t n, int32_t c, const float* scale, c
 int tl_bn_relu_bwd(const float* x, const float* d_act, int64_t n, int32_t c, const float* scale, const float* shift,
                    const float* mean, const float* invstd, int32_t batch_stats, double* acc, float* dx, float* dgamma,
                    float* dbeta, void* stream);
+/* Pack a conv parameter (spconv KRSC layout [C_out][n_off][C_in], fp32) into the tcgen05 B-operand image that tl_conv_fwd
+ * modes 1/2 read: forward layout (transpose = 0) or the data-gradient layout (transpose = 1: C_in/C_out swapped, offsets
+ * mirrored when `mirror`); fp16 (`half`) or TF32-rounded fp32; bk = channels per chunk (32, or 64 for fp16 with C_in' % 64 == 0). */
+int tl_pack_weight_tc(const float* w, int32_t c_out, int32_t n_off, int32_t c_in, int32_t transpose, int32_t mirror,
+                      int32_t half, int32_t bk, void* out, void* stream);
 /* dw[k][ci][co] = sum_r src[index[k][r], ci] * d_out[r, co]   (index NULL => identity, n_off == 1); dw is overwritten */
 int tl_conv_wgrad(const float* src, int64_t src_stride, int32_t c_in, int32_t n_off, const int32_t* index,
                   int64_t index_stride, const uint32_t* tile_mask, const float* d_out, int64_t n_out, int32_t c_out,

@@ -102,6 +102,26 @@ def test_bn_relu_forward_backward_and_running_stats_vs_torch(n, c, training):
     assert int(bn.num_batches_tracked) == int(bn_ref.num_batches_tracked)
 
 
+@pytest.mark.parametrize('co,ci,k', [(32, 32, 27), (64, 32, 8), (96, 160, 27), (32, 64, 1)])
+def test_pack_weight_kernel_matches_host_packing_bit_exact(co, ci, k):
+    from treelearn_b200._lib import check, ptr, stream_ptr
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(co + ci + k)
+    w = torch.randn((co, k, ci), generator=g).cuda()                       # spconv KRSC parameter layout, K flattened
+    for transpose, mirror, half, bk in [(0, 0, 0, 32), (1, 1, 0, 32), (1, 0, 0, 32), (0, 0, 1, 32), (0, 0, 1, 64), (1, 1, 1, 64)]:
+        co_p, ci_p = (ci, co) if transpose else (co, ci)
+        if ci_p % bk:
+            continue
+        ref_in = w.permute(1, 2, 0) if transpose else w.permute(1, 0, 2)   # [K, C_out', C_in']
+        if transpose and mirror:
+            ref_in = ref_in.flip(0)
+        ref = sparse.pack_weight_tc(ref_in, bool(half), bk)
+        out = torch.empty((k, ci_p // bk, co_p, bk), dtype=torch.float16 if half else torch.float32, device='cuda')
+        check(lib.tl_pack_weight_tc(ptr(w), co, k, ci, transpose, mirror, half, bk, ptr(out), stream_ptr()))
+        assert torch.equal(out.view(torch.int16 if half else torch.int32), ref.view(torch.int16 if half else torch.int32)), \
+            (transpose, mirror, half, bk)
+
+
 def _fixture():
     g = np.load(os.path.join(GOLD, 'model_small.npz'))
     sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith('sd:')}

@@ -60,20 +60,34 @@ def _round_tf32(w):
     return ((i + 0x0FFF + ((i >> 13) & 1)) & ~0x1FFF).view(torch.float32)
 
 
-def _pack(w_kco_ci, c_in, c_out, mode):
-    """w [K, C_out, C_in] (K-major B operand) -> the layout tl_conv_fwd wants for (mode, shape); returns (w, mode)."""
-    if mode != _lib.MODE_FP32 and _tc_ok(c_in, c_out):
-        return sparse.pack_weight_tc(w_kco_ci, False), _lib.MODE_TF32
-    return w_kco_ci.permute(0, 2, 1).contiguous(), _lib.MODE_FP32      # SIMT layout [K, C_in, C_out]
+def pack_param(weight, transpose, mirror, mode):
+    """Conv parameter [C_out, k, k, k, C_in] -> (packed weights, kernel mode) for tl_conv_fwd.
+    transpose=False: the forward conv; transpose=True: the data-gradient conv (C_in/C_out swapped, offsets mirrored when
+    `mirror`).  tcgen05-eligible shapes are packed by one CUDA kernel (tl_pack_weight_tc, TF32-rounded fp32); the rest take
+    the fp32 SIMT layout [K, C_in', C_out']."""
+    co, ci = weight.shape[0], weight.shape[-1]
+    k = w_noff(weight)
+    co_p, ci_p = (ci, co) if transpose else (co, ci)
+    w = weight.detach().float().contiguous()
+    if mode != _lib.MODE_FP32 and _tc_ok(ci_p, co_p):
+        out = torch.empty((k, ci_p // 32, co_p, 32), dtype=torch.float32, device=w.device)
+        check(_lib.load().tl_pack_weight_tc(ptr(w), co, k, ci, int(transpose), int(mirror), 0, 32, ptr(out), stream_ptr()))
+        return out, _lib.MODE_TF32
+    w3 = w.reshape(co, k, ci)
+    if not transpose:
+        return w3.permute(1, 2, 0).contiguous(), _lib.MODE_FP32        # [K, C_in, C_out]
+    wt = w3.permute(1, 0, 2)                                           # [K, C_in' = C_out, C_out' = C_in]
+    if mirror:
+        wt = wt.flip(0)
+    return wt.contiguous(), _lib.MODE_FP32
 
 
 class _SparseConv(torch.autograd.Function):
     @staticmethod
     def forward(ctx, src, weight, geom, mode):
         src = src.contiguous().float()
-        co, ci = weight.shape[0], weight.shape[-1]
-        w = weight.detach().float().reshape(co, -1, ci)                 # [Co, K, Ci]
-        wp, m = _pack(w.permute(1, 0, 2), ci, co, mode)
+        co = weight.shape[0]
+        wp, m = pack_param(weight, False, False, mode)
         out = sparse.conv([Seg(src, wp, geom.index, geom.mask)], geom.n_out, co, m, raw=True)
         ctx.save_for_backward(src, weight)
         ctx.geom, ctx.mode = geom, mode
@@ -87,11 +101,7 @@ class _SparseConv(torch.autograd.Function):
         co, ci = weight.shape[0], weight.shape[-1]
         d_src = d_w = None
         if ctx.needs_input_grad[0]:
-            w = weight.detach().float().reshape(co, -1, ci)             # [Co, K, Ci]
-            wt = w.permute(1, 2, 0)                                     # dgrad conv: [K, C_out'=Ci, C_in'=Co]
-            if geom.mirror:
-                wt = wt.flip(0)
-            wp, m = _pack(wt, co, ci, mode)
+            wp, m = pack_param(weight, True, geom.mirror, mode)
             d_src = sparse.conv([Seg(d_out, wp, geom.index_t, geom.mask_t)], geom.n_in, ci, m, raw=True)
         if ctx.needs_input_grad[1]:
             n_off = w_noff(weight)

@@ -5,6 +5,8 @@
 // Reference semantics: torch.nn.BatchNorm1d(eps=1e-4, momentum=0.1) applied to SparseConvTensor.features
 // (tree_learn/model/tree_learn.py:34, blocks.py:57-70): normalise with the biased batch variance, update the
 // running variance with the unbiased one; autograd backward (tools/training/train.py:40).
+#include <cuda_fp16.h>
+
 #include "tl_common.cuh"
 
 namespace tl {
@@ -165,13 +167,15 @@ __global__ void __launch_bounds__(64) k_conv_wgrad(const float* __restrict__ src
 #pragma unroll
         for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
     const int lrow = tid >> 3, lc = (tid & 7) * 4;   // loader: 8 rows x 8 float4 per pass, 4 passes
-    for (int64_t rb = r_begin; rb < r_end; rb += WG_ROWS) {
-        if (index && tile_mask && !((tile_mask[rb / TL_TILE_ROWS] >> k) & 1u)) continue;   // block-uniform (rb % 32 == 0)
-        __syncthreads();
+    // software pipeline: the rows of batch i+1 are fetched into registers while batch i is multiplied out of shared memory
+    float4 xr[4], yr[4];
+    auto live = [&](int64_t rb) {   // block-uniform: does the 128-row tile of this batch have offset k at all?
+        return !(index && tile_mask) || ((tile_mask[rb / TL_TILE_ROWS] >> k) & 1u);
+    };
+    auto fetch = [&](int64_t rb) {
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
-            const int rr = p * 8 + lrow;
-            const int64_t r = rb + rr;
+            const int64_t r = rb + p * 8 + lrow;
             float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), yv = xv;
             if (r < r_end) {
                 const int64_t s = index ? (int64_t)__ldg(index + (int64_t)k * index_stride + r) : r;
@@ -192,10 +196,25 @@ __global__ void __launch_bounds__(64) k_conv_wgrad(const float* __restrict__ src
                     }
                 }
             }
-            *reinterpret_cast<float4*>(&xs[rr][lc]) = xv;
-            *reinterpret_cast<float4*>(&ys[rr][lc]) = yv;
+            xr[p] = xv, yr[p] = yv;
+        }
+    };
+    auto next_live = [&](int64_t rb) {
+        while (rb < r_end && !live(rb)) rb += WG_ROWS;
+        return rb;
+    };
+    int64_t rb = next_live(r_begin);
+    if (rb < r_end) fetch(rb);
+    while (rb < r_end) {
+        __syncthreads();
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            *reinterpret_cast<float4*>(&xs[p * 8 + lrow][lc]) = xr[p];
+            *reinterpret_cast<float4*>(&ys[p * 8 + lrow][lc]) = yr[p];
         }
         __syncthreads();
+        const int64_t nb = next_live(rb + WG_ROWS);
+        if (nb < r_end) fetch(nb);
 #pragma unroll 8
         for (int rr = 0; rr < WG_ROWS; ++rr) {
             const float4 a = *reinterpret_cast<const float4*>(&xs[rr][ti * 4]);
@@ -206,6 +225,7 @@ __global__ void __launch_bounds__(64) k_conv_wgrad(const float* __restrict__ src
 #pragma unroll
                 for (int v = 0; v < 4; ++v) acc[u][v] = fmaf(av[u], bv[v], acc[u][v]);
         }
+        rb = nb;
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -215,6 +235,46 @@ __global__ void __launch_bounds__(64) k_conv_wgrad(const float* __restrict__ src
         for (int v = 0; v < 4; ++v) {
             const int co = co0 + tj * 4 + v;
             if (co < c_out && acc[u][v] != 0.f) atomicAdd(dw + ((int64_t)k * c_in + ci) * c_out + co, acc[u][v]);
+        }
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// weight packing for the tcgen05 paths (training repacks every conv twice per step: forward and data-gradient layout)
+//   src: the parameter, spconv KRSC layout [C_out][K][C_in] fp32
+//   dst: [K][rows_k / ... ] B-operand image [K][c_in'/bk][c_out'][bk] with the UMMA swizzle applied per row
+//        (sparse.pack_weight_tc), where for the forward conv (c_out', c_in') = (C_out, C_in) and element
+//        (k, n, c) = W[n][k][c]; for the data gradient (transpose = 1) (c_out', c_in') = (C_in, C_out) and
+//        (k, n, c) = W[c][mirror ? K-1-k : k][n].   fp32 rounded to TF32 (RN-even) or fp16.
+// ------------------------------------------------------------------------------------------------
+template <bool HALF>
+__global__ void __launch_bounds__(256) k_pack_weight_tc(const float* __restrict__ w, int c_out, int n_off, int c_in,
+                                                        int transpose, int mirror, int bk, void* __restrict__ out) {
+    const int co_p = transpose ? c_in : c_out, ci_p = transpose ? c_out : c_in;     // packed conv's C_out', C_in'
+    const int64_t total = (int64_t)n_off * co_p * ci_p;
+    const int eb = HALF ? 2 : 4, epc = 16 / eb, ch = bk / epc;                       // elements per 16 B chunk, chunks per row
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        // destination coordinates: [k][kb][n][chunk][elem]
+        int64_t t = e;
+        const int el = (int)(t % epc);
+        t /= epc;
+        const int cdst = (int)(t % ch);
+        t /= ch;
+        const int n = (int)(t % co_p);
+        t /= co_p;
+        const int kb = (int)(t % (ci_p / bk));
+        const int k = (int)(t / (ci_p / bk));
+        const int x = (bk * eb == 128) ? (n & 7) : ((n >> 1) & 3);
+        const int c = kb * bk + (cdst ^ x) * epc + el;                               // source channel of the packed conv
+        const int ks = (transpose && mirror) ? n_off - 1 - k : k;
+        const float v = transpose ? w[((int64_t)c * n_off + ks) * c_in + n] : w[((int64_t)n * n_off + ks) * c_in + c];
+        if (HALF) {
+            reinterpret_cast<__half*>(out)[e] = __float2half_rn(v);
+        } else {
+            uint32_t i = __float_as_uint(v);
+            i = (i + 0x0FFFu + ((i >> 13) & 1u)) & ~0x1FFFu;                         // round to nearest even at 10 mantissa bits
+            reinterpret_cast<uint32_t*>(out)[e] = i;
         }
     }
 }
@@ -301,6 +361,20 @@ int tl_conv_wgrad(const float* src, int64_t src_stride, int32_t c_in, int32_t n_
     dim3 grid((unsigned)((n_out + rpb - 1) / rpb), (unsigned)n_off, (unsigned)(ci_tiles * co_tiles));
     train::k_conv_wgrad<<<grid, 64, 0, stream>>>(src, src_stride, c_in, n_off, index, index_stride, tile_mask, d_out,
                                                  n_out, c_out, rpb, co_tiles, dw);
+    TL_LAUNCH_CHECK();
+    return TL_OK;
+}
+
+int tl_pack_weight_tc(const float* w, int32_t c_out, int32_t n_off, int32_t c_in, int32_t transpose, int32_t mirror,
+                      int32_t half, int32_t bk, void* out, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int co_p = transpose ? c_in : c_out, ci_p = transpose ? c_out : c_in;
+    TL_REQUIRE(w && out && n_off >= 1 && (bk == 32 || bk == 64) && ci_p % bk == 0 && co_p % 32 == 0,
+               "tl_pack_weight_tc: c_out=%d n_off=%d c_in=%d transpose=%d bk=%d", c_out, n_off, c_in, transpose, bk);
+    const int64_t total = (int64_t)n_off * c_out * c_in;
+    const unsigned grid = (unsigned)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+    if (half) train::k_pack_weight_tc<true><<<grid, 256, 0, stream>>>(w, c_out, n_off, c_in, transpose, mirror, bk, out);
+    else train::k_pack_weight_tc<false><<<grid, 256, 0, stream>>>(w, c_out, n_off, c_in, transpose, mirror, bk, out);
     TL_LAUNCH_CHECK();
     return TL_OK;
 }
