@@ -1,6 +1,7 @@
 """Timeline of the k_conv_tc ring on SM 0 (TL_TC_DEBUG bit 32) for one level-0 32->32 conv of the cfg2 tile:
 per slot fill: gather wait / issue, data latency, MMA issue, slot-free latency.  Run on the GPU box:
-    TL_TC_DEBUG=32 python tools/trace_conv.py"""
+    make -C treelearn_b200/csrc clean all TRACE=1 && TL_TC_DEBUG=32 python tools/trace_conv.py [32|64]
+(the hooks are compiled out of the default build)"""
 import ctypes as C
 import os
 import sys

@@ -277,8 +277,14 @@ __device__ __forceinline__ uint2 ld_shared_u2(uint32_t addr) {
 // the slot round trip can be split into issue / data latency / MMA / barrier hops (tools/trace_conv.py)
 constexpr int TRACE_ROLES = 8, TRACE_LEN = 2048;
 __device__ unsigned long long g_trace[TRACE_ROLES * TRACE_LEN];
+// Compiled in only with -DTL_TC_TRACE=1 (make TRACE=1): the hooks cost registers in the gather loop otherwise.
+#ifdef TL_TC_TRACE
+constexpr bool kTrace = true;
+#else
+constexpr bool kTrace = false;
+#endif
 __device__ __forceinline__ void trace(bool on, int role, uint32_t& pos, uint32_t tag) {
-    if (on && pos < TRACE_LEN) {
+    if (kTrace && on && pos < TRACE_LEN) {
         g_trace[role * TRACE_LEN + pos] = ((unsigned long long)tag << 48) | ((unsigned long long)clock64() & 0xffffffffffffull);
         ++pos;
     }
@@ -543,7 +549,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const tl_conv_desc d, c
         uint32_t prev_s = 0xffffffffu;
         uint64_t seg_src = 0;
         uint32_t seg_stride = 0, seg_idx = 0xffffffffu;
-        const bool tr = (P.debug & 32) && blockIdx.x == 0 && gw == 0 && lane == 0 && group < 4;
+        const bool tr = kTrace && (P.debug & 32) && blockIdx.x == 0 && gw == 0 && lane == 0 && group < 4;
         uint32_t tpos = 0;
         for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++witer) {
             const int tile = w / P.splits;
@@ -744,7 +750,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const tl_conv_desc d, c
             const uint32_t b_step = L.b_stage_bytes >> 4;
             const uint32_t wmask = (uint32_t)(P.acc_ways - 1);
             uint32_t slot = 0, phase = 0, titer = 0;
-            const bool trm = (P.debug & 32) && blockIdx.x == 0 && lane == 0;
+            const bool trm = kTrace && (P.debug & 32) && blockIdx.x == 0 && lane == 0;
             uint32_t tposm = 0, fill_no = 0;
             for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++titer) {
                 const uint32_t buf = titer & 1u;          // TMEM accumulator buffer
