@@ -395,9 +395,10 @@ __device__ __forceinline__ void knn_scan_cell(const KnnGrid& g, const KnnLevel& 
 // distance is within the radius that level has provably covered.
 __global__ void __launch_bounds__(128) k_knn_vote(const float* __restrict__ query, int64_t nq, const KnnGrid g,
                                                   const int64_t* __restrict__ ref_labels, int k,
-                                                  int64_t* __restrict__ out) {
-    int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (q >= nq) return;
+                                                  const int* __restrict__ order, int64_t* __restrict__ out) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= nq) return;
+    const int64_t q = order ? order[t] : t;     // queries in cell order: the lanes of a warp scan the same cells
     const float qx = query[q * 3], qy = query[q * 3 + 1], qz = query[q * 3 + 2];
     const int fx = knn_fine_index(qx), fy = knn_fine_index(qy), fz = knn_fine_index(qz);
     TopK top;
@@ -693,14 +694,17 @@ int tl_cluster_radius_cc(const float* points_xy, int64_t n, double radius, int64
 }
 
 size_t tl_knn_workspace_bytes(int64_t n_ref, int64_t n_query) {
-    (void)n_query;
     if (n_ref <= 0) return 256;
     const uint64_t cap = table_capacity(n_ref);
     size_t cub_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (uint64_t*)nullptr, (uint64_t*)nullptr, (int*)nullptr, (int*)nullptr,
                                     (int)n_ref);
+    size_t cub_q = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, cub_q, (uint64_t*)nullptr, (uint64_t*)nullptr, (int*)nullptr, (int*)nullptr,
+                                    (int)(n_query > 0 ? n_query : 1));
     return 2 * align_up(n_ref * 8) + 2 * align_up(n_ref * 4) + align_up(n_ref * 16) +
-           kKnnLevels * (align_up(cap * 8) + align_up(cap * 4)) + align_up(cub_bytes) + 4096;
+           kKnnLevels * (align_up(cap * 8) + align_up(cap * 4)) + align_up(cub_bytes) + align_up(cub_q) +
+           2 * align_up(n_query * 8) + 2 * align_up(n_query * 4) + 8192;
 }
 
 int tl_knn_vote(const float* ref_xyz, const int64_t* ref_labels, int64_t n_ref, const float* query_xyz, int64_t n_query,
@@ -741,7 +745,27 @@ int tl_knn_vote(const float* ref_xyz, const int64_t* ref_labels, int64_t n_ref, 
         TL_LAUNCH_CHECK();
         g.level[l] = KnnLevel{tkeys[l], tvals[l], cap - 1, 6 * l, rings[l]};
     }
-    k_knn_vote<<<(unsigned)((n_query + 127) / 128), 128, 0, stream>>>(query_xyz, n_query, g, ref_labels, k, out_labels);
+    // queries sorted by the same hierarchical cell key: warps then scan the same cells (less divergence, cache hits)
+    const int* order = nullptr;
+    if (n_query >= 4096 && n_query < (1ll << 31)) {
+        uint64_t* qk_in = c.take<uint64_t>(n_query);
+        uint64_t* qk_out = c.take<uint64_t>(n_query);
+        int* qi_in = c.take<int>(n_query);
+        int* qi_out = c.take<int>(n_query);
+        size_t cub_q = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, cub_q, (uint64_t*)nullptr, (uint64_t*)nullptr, (int*)nullptr, (int*)nullptr,
+                                        (int)n_query);
+        void* cub_tmp_q = c.take<char>(cub_q);
+        if (c.ok()) {
+            const unsigned nbq = (unsigned)((n_query + T - 1) / T);
+            k_knn_keys<<<nbq, T, 0, stream>>>(query_xyz, n_query, qk_in, qi_in);
+            TL_LAUNCH_CHECK();
+            TL_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(cub_tmp_q, cub_q, qk_in, qk_out, qi_in, qi_out, (int)n_query, 0,
+                                                          3 * kFineBits, stream));
+            order = qi_out;
+        }
+    }
+    k_knn_vote<<<(unsigned)((n_query + 127) / 128), 128, 0, stream>>>(query_xyz, n_query, g, ref_labels, k, order, out_labels);
     TL_LAUNCH_CHECK();
     return TL_OK;
 }

@@ -14,6 +14,7 @@ There is no CPU path: tensors are moved to the current CUDA device (like the ref
 `cuda_cast`, tree_learn/util/train.py:28-43) and the extension must be present.
 """
 import functools
+import os
 
 import torch
 import torch.nn.functional as F
@@ -83,6 +84,9 @@ class TreeLearn(nn.Module):
         self.planes = [channels * (i + 1) for i in range(num_blocks)]
         self._norm = functools.partial(nn.BatchNorm1d, eps=BN_EPS, momentum=BN_MOMENTUM)
         self._packed = None
+        # measured on B200 (cfg2): building levels >= 1 on a side stream next to the level-0 convs gains nothing (17.10 vs 16.96 ms:
+        # the persistent conv CTAs leave the small geometry kernels no room to run concurrently) -> off by default
+        self.overlap_geometry = os.environ.get('TL_OVERLAP_GEOMETRY', '0') != '0'
 
         self._put('input_conv.0', SparseConvWeight(dim_coord + dim_feat, channels, 3))
         self._declare_ublock('unet', 0)
@@ -208,9 +212,12 @@ class TreeLearn(nn.Module):
             shape = [int(s) for s in self.spatial_shape]
         else:
             shape = (vcoords[:, 1:].max(dim=0).values + 1).tolist()   # reference tree_learn.py:165
-        levels = sparse.build_levels(keys, vcoords, shape, self.num_blocks)
         if self._needs_autograd_path():
+            levels = sparse.build_levels(keys, vcoords, shape, self.num_blocks)
             return self._train_backbone(vfeats, levels), v2p
+        # inference: levels >= 1 are built on a side stream while the level-0 convolutions already run
+        levels = sparse.LazyLevels(keys, vcoords, shape, self.num_blocks) if self.overlap_geometry \
+            else sparse.build_levels(keys, vcoords, shape, self.num_blocks)
         return self._run_backbone(vfeats, levels), v2p
 
     def _needs_autograd_path(self):

@@ -73,10 +73,19 @@ def voxelize(coords, input_feats, batch_ids, batch_size, voxel_size=0.1, use_coo
 def build_levels(keys, coords, spatial_shape, num_levels, subm=True):
     """Level pyramid (strided k2/s2 maps) + 3^3 rulebook per level.  Raises ValueError('... reach zero!!! ...')
     like spconv when an axis of the U-Net collapses (tree_learn/util/pipeline.py:91-97)."""
-    lib = _lib.load()
-    dev = keys.device
     levels = [Level(n=int(keys.shape[0]), shape=[int(s) for s in spatial_shape], keys=keys, coords=coords)]
-    for l in range(num_levels - 1):
+    _extend_levels(levels, num_levels)
+    if subm:
+        for lv in levels:
+            build_subm_rulebook(lv)
+    return levels
+
+
+def _extend_levels(levels, num_levels):
+    """Append the coarser levels (strided maps of levels[-1] ... ) until there are `num_levels`."""
+    lib = _lib.load()
+    dev = levels[0].keys.device
+    for l in range(len(levels) - 1, num_levels - 1):
         fine = levels[-1]
         n = fine.n
         stride = pad_rows(n)
@@ -102,10 +111,55 @@ def build_levels(keys, coords, spatial_shape, num_levels, subm=True):
                                  ptr(fine.down_mask), ptr(fine.up_index), ptr(fine.up_mask), cshape, C.byref(nc),
                                  ptr(ws), wsb, stream_ptr()))
         levels.append(Level(n=nc.value, shape=list(cshape), keys=ckeys[:nc.value], coords=ccoords[:nc.value]))
-    if subm:
-        for lv in levels:
-            build_subm_rulebook(lv)
     return levels
+
+
+class LazyLevels:
+    """Level pyramid whose coarser levels are built late and on a side stream.
+
+    Level 0 and its 3^3 rulebook are built at construction on the current stream.  The strided maps and the rulebooks of
+    levels >= 1 are built on first access of any level >= 1 -- by then the caller has already enqueued the level-0
+    convolutions on the main stream, so the ~1.2 ms of hash / scan / probe kernels (and their host synchronisations) run
+    concurrently with them on the side stream; the main stream then waits on one event.  (The conv kernel keeps one CTA
+    per SM with ~190 KB of shared memory; the small geometry kernels fit beside it.)"""
+    _side = {}
+
+    def __init__(self, keys, coords, spatial_shape, num_levels):
+        self.num_levels = num_levels
+        self.levels = [Level(n=int(keys.shape[0]), shape=[int(s) for s in spatial_shape], keys=keys, coords=coords)]
+        build_subm_rulebook(self.levels[0])
+        self._done = num_levels <= 1
+
+    def _finish(self):
+        if self._done:
+            return
+        self._done = True
+        main = torch.cuda.current_stream()
+        dev = self.levels[0].keys.device
+        side = LazyLevels._side.get(dev.index)
+        if side is None:
+            side = LazyLevels._side[dev.index] = torch.cuda.Stream(device=dev)
+        with torch.cuda.stream(side):
+            _extend_levels(self.levels, self.num_levels)
+            for lv in self.levels[1:]:
+                build_subm_rulebook(lv)
+        main.wait_stream(side)
+        for lv in self.levels:        # tensors allocated under the side stream are consumed by main-stream kernels
+            for t in (lv.keys, lv.coords, lv.nbr, lv.nbr_mask, lv.down_index, lv.down_mask, lv.up_index, lv.up_mask):
+                if t is not None:
+                    t.record_stream(main)
+
+    def __len__(self):
+        return self.num_levels
+
+    def __getitem__(self, l):
+        if l != 0:
+            self._finish()
+        return self.levels[l]
+
+    def __iter__(self):
+        self._finish()
+        return iter(self.levels)
 
 
 def build_subm_rulebook(lv):
