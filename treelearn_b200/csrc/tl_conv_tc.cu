@@ -92,9 +92,6 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32
 __device__ __forceinline__ void cp_async16_cg(uint32_t dst, const void* src, uint32_t src_bytes) {   // L2 only
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
-__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
-}
 __device__ __forceinline__ int ld_shared_i32(uint32_t addr) {
     int v;
     asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
@@ -104,24 +101,6 @@ __device__ __forceinline__ int ld_shared_i32(uint32_t addr) {
 __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-// wait until at most `n` of this thread's cp.async groups are pending (n is warp-uniform)
-__device__ __forceinline__ void cp_async_wait_dyn(int n) {
-    switch (n) {
-        case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
-        case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
-        case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
-        case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
-        case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
-        case 5: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
-        case 6: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
-        case 7: asm volatile("cp.async.wait_group 7;" ::: "memory"); break;
-        case 8: asm volatile("cp.async.wait_group 8;" ::: "memory"); break;
-        case 9: asm volatile("cp.async.wait_group 9;" ::: "memory"); break;
-        default: asm volatile("cp.async.wait_group 10;" ::: "memory"); break;
-    }
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -209,29 +188,6 @@ __device__ __forceinline__ float round_tf32(float v) {
     return __uint_as_float(r);
 }
 
-// relu(scale*v+shift) of 32 consecutive columns -> the consumer's operand format: TF32-rounded fp32 or fp16
-template <int EB>
-__device__ __forceinline__ void store_act32(void* out, int64_t elem_off, const float (&v)[32], const float* __restrict__ sc,
-                                            const float* __restrict__ sh) {
-    float a[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) a[j] = fmaxf(fmaf(v[j], __ldg(sc + j), __ldg(sh + j)), 0.f);
-    if (EB == 4) {
-        float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + elem_off);
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-            op[j] = make_float4(round_tf32(a[4 * j]), round_tf32(a[4 * j + 1]), round_tf32(a[4 * j + 2]), round_tf32(a[4 * j + 3]));
-    } else {
-        uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(out) + elem_off);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            __half2 h0 = __floats2half2_rn(a[8 * j], a[8 * j + 1]), h1 = __floats2half2_rn(a[8 * j + 2], a[8 * j + 3]);
-            __half2 h2 = __floats2half2_rn(a[8 * j + 4], a[8 * j + 5]), h3 = __floats2half2_rn(a[8 * j + 6], a[8 * j + 7]);
-            op[j] = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
-                               *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
-        }
-    }
-}
 // 4 consecutive activated columns -> the consumer's operand format (16 B of TF32-rounded fp32 or 8 B of fp16)
 template <int EB>
 __device__ __forceinline__ void store_act4(void* out, int64_t e, float a0, float a1, float a2, float a3) {
