@@ -185,10 +185,11 @@ int tl_bn_relu_bwd(const float* x, const float* d_act, int64_t n, int32_t c, con
  * mirrored when `mirror`); fp16 (`half`) or TF32-rounded fp32; bk = channels per chunk (32, or 64 for fp16 with C_in' % 64 == 0). */
 int tl_pack_weight_tc(const float* w, int32_t c_out, int32_t n_off, int32_t c_in, int32_t transpose, int32_t mirror,
                       int32_t half, int32_t bk, void* out, void* stream);
-/* dw[k][ci][co] = sum_r src[index[k][r], ci] * d_out[r, co]   (index NULL => identity, n_off == 1); dw is overwritten */
+/* dw[k][ci][co] = sum_r src[index[k][r], ci] * d_out[r, co]   (index NULL => identity, n_off == 1); dw is overwritten.
+ * tf32 = 0: fp32 FMA (exact-arithmetic training mode); tf32 = 1: TF32 tensor-core products, fp32 accumulation. */
 int tl_conv_wgrad(const float* src, int64_t src_stride, int32_t c_in, int32_t n_off, const int32_t* index,
                   int64_t index_stride, const uint32_t* tile_mask, const float* d_out, int64_t n_out, int32_t c_out,
-                  float* dw, void* stream);
+                  float* dw, int32_t tf32, void* stream);
 
 #ifdef __cplusplus
 }

@@ -42,9 +42,9 @@ def test_subm_conv_grads_vs_oracle_autograd(ci, co, mode):
     ag.sparse_conv(xc, wc, ag.subm_geom(lv), m).backward(gy.cuda())
     tol = GRAD_TOL if mode == 'fp32' else dict(atol=2e-2, rtol=2e-2)   # TF32 operands (10-bit mantissa) in fwd/dgrad
     assert torch.allclose(xc.grad.cpu(), xr.grad, **tol)
-    # wgrad always accumulates in fp32 SIMT: tight in both modes relative to its scale (sum over ~1e4 rows)
+    # wgrad: fp32 FMA in fp32 mode (tight); TF32 tensor-core products with fp32 accumulation in tf32 mode
     scale = wr.grad.abs().max().item()
-    assert (wc.grad.cpu() - wr.grad).abs().max().item() < 2e-4 * max(scale, 1.0)
+    assert (wc.grad.cpu() - wr.grad).abs().max().item() < (2e-4 if mode == 'fp32' else 5e-3) * max(scale, 1.0)
 
 
 def test_strided_inverse_and_1x1_grads_vs_oracle_autograd():

@@ -64,7 +64,7 @@ SIGNATURES = {
     'tl_bn_relu_apply': (C.c_int, [_P, _I64, _I32, _P, _P, _P, _P]),
     'tl_bn_relu_bwd': (C.c_int, [_P, _P, _I64, _I32, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _P]),
     'tl_pack_weight_tc': (C.c_int, [_P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P]),
-    'tl_conv_wgrad': (C.c_int, [_P, _I64, _I32, _I32, _P, _I64, _P, _P, _I64, _I32, _P, _P]),
+    'tl_conv_wgrad': (C.c_int, [_P, _I64, _I32, _I32, _P, _I64, _P, _P, _I64, _I32, _P, _I32, _P]),
 }
 
 _lib = None

@@ -109,7 +109,7 @@ class _SparseConv(torch.autograd.Function):
             lib = _lib.load()
             idx = geom.index
             check(lib.tl_conv_wgrad(ptr(src), src.stride(0), ci, n_off, ptr(idx), 0 if idx is None else idx.stride(0),
-                                    ptr(geom.mask), ptr(d_out), geom.n_out, co, ptr(dw), stream_ptr()))
+                                    ptr(geom.mask), ptr(d_out), geom.n_out, co, ptr(dw), int(mode != _lib.MODE_FP32), stream_ptr()))
             d_w = dw.permute(2, 0, 1).reshape(weight.shape).to(weight.dtype)
         return d_src, d_w, None, None
 

@@ -240,6 +240,112 @@ __global__ void __launch_bounds__(64) k_conv_wgrad(const float* __restrict__ src
 }
 
 
+// TF32 tensor-core variant (mma.sync.m16n8k8, fp32 accumulate) of the weight gradient, used by the tf32 / f16 training
+// modes: same tiling and software pipeline as k_conv_wgrad; warp w owns 16 of the 32 input channels (M), all 32 output
+// channels (4 N tiles of 8), K = the 32 staged rows in 4 steps of 8.  Operands are rounded to TF32 (RN) when staged.
+// Rows are padded to 40 floats so that the fragment loads (lane = 4*group + tig -> row tig, column group) are conflict-free.
+constexpr int WG_PAD = 40;
+__device__ __forceinline__ float to_tf32(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+__global__ void __launch_bounds__(64) k_conv_wgrad_tf32(const float* __restrict__ src, int64_t src_stride, int c_in, int n_off,
+                                                        const int32_t* __restrict__ index, int64_t index_stride,
+                                                        const uint32_t* __restrict__ tile_mask,
+                                                        const float* __restrict__ d_out, int64_t n_out, int c_out,
+                                                        int rows_per_block, int co_tiles, float* __restrict__ dw) {
+    __shared__ __align__(16) float xs[WG_ROWS][WG_PAD];
+    __shared__ __align__(16) float ys[WG_ROWS][WG_PAD];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, grp = lane >> 2, tig = lane & 3;
+    const int k = blockIdx.y;
+    const int ci0 = (blockIdx.z / co_tiles) * 32, co0 = (blockIdx.z % co_tiles) * 32;
+    const int64_t r_begin = (int64_t)blockIdx.x * rows_per_block;
+    const int64_t r_end = min(r_begin + (int64_t)rows_per_block, n_out);
+    float acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+    const int lrow = tid >> 3, lc = (tid & 7) * 4;   // loader: 8 rows x 8 float4 per pass, 4 passes
+    float4 xr[4], yr[4];
+    auto live = [&](int64_t rb) { return !(index && tile_mask) || ((tile_mask[rb / TL_TILE_ROWS] >> k) & 1u); };
+    auto fetch = [&](int64_t rb) {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const int64_t r = rb + p * 8 + lrow;
+            float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), yv = xv;
+            if (r < r_end) {
+                const int64_t s = index ? (int64_t)__ldg(index + (int64_t)k * index_stride + r) : r;
+                if (s >= 0) {
+                    const float* xp = src + s * src_stride + ci0 + lc;
+                    const float* yp = d_out + r * c_out + co0 + lc;
+                    if (ci0 + lc + 3 < c_in) xv = __ldg(reinterpret_cast<const float4*>(xp));
+                    else {
+                        if (ci0 + lc < c_in) xv.x = __ldg(xp);
+                        if (ci0 + lc + 1 < c_in) xv.y = __ldg(xp + 1);
+                        if (ci0 + lc + 2 < c_in) xv.z = __ldg(xp + 2);
+                    }
+                    if (co0 + lc + 3 < c_out) yv = __ldg(reinterpret_cast<const float4*>(yp));
+                    else {
+                        if (co0 + lc < c_out) yv.x = __ldg(yp);
+                        if (co0 + lc + 1 < c_out) yv.y = __ldg(yp + 1);
+                        if (co0 + lc + 2 < c_out) yv.z = __ldg(yp + 2);
+                    }
+                }
+            }
+            xr[p] = xv, yr[p] = yv;
+        }
+    };
+    auto next_live = [&](int64_t rb) {
+        while (rb < r_end && !live(rb)) rb += WG_ROWS;
+        return rb;
+    };
+    int64_t rb = next_live(r_begin);
+    if (rb < r_end) fetch(rb);
+    while (rb < r_end) {
+        __syncthreads();
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            *reinterpret_cast<float4*>(&xs[p * 8 + lrow][lc]) =
+                make_float4(to_tf32(xr[p].x), to_tf32(xr[p].y), to_tf32(xr[p].z), to_tf32(xr[p].w));
+            *reinterpret_cast<float4*>(&ys[p * 8 + lrow][lc]) =
+                make_float4(to_tf32(yr[p].x), to_tf32(yr[p].y), to_tf32(yr[p].z), to_tf32(yr[p].w));
+        }
+        __syncthreads();
+        const int64_t nb = next_live(rb + WG_ROWS);
+        if (nb < r_end) fetch(nb);
+#pragma unroll
+        for (int ks = 0; ks < WG_ROWS; ks += 8) {
+            // A[m = ci][k = row] = xs[row][ci]: a0 (m = grp, k = tig), a1 (m = grp + 8, k = tig), a2 / a3: k + 4
+            const uint32_t a0 = __float_as_uint(xs[ks + tig][warp * 16 + grp]);
+            const uint32_t a1 = __float_as_uint(xs[ks + tig][warp * 16 + grp + 8]);
+            const uint32_t a2 = __float_as_uint(xs[ks + tig + 4][warp * 16 + grp]);
+            const uint32_t a3 = __float_as_uint(xs[ks + tig + 4][warp * 16 + grp + 8]);
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                // B[k = row][n = co] = ys[row][co]: b0 (k = tig, n = grp), b1 (k = tig + 4, n = grp)
+                const uint32_t b0 = __float_as_uint(ys[ks + tig][nt * 8 + grp]);
+                const uint32_t b1 = __float_as_uint(ys[ks + tig + 4][nt * 8 + grp]);
+                asm volatile(
+                    "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+                    "{%0, %1, %2, %3};"
+                    : "+f"(acc[nt][0]), "+f"(acc[nt][1]), "+f"(acc[nt][2]), "+f"(acc[nt][3])
+                    : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+            }
+        }
+        rb = nb;
+    }
+    // D fragment: c0 (m = grp, n = 2 tig), c1 (m = grp, n = 2 tig + 1), c2 / c3: m + 8
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int ci = ci0 + warp * 16 + grp + (e >> 1) * 8, co = co0 + nt * 8 + 2 * tig + (e & 1);
+            if (ci < c_in && co < c_out && acc[nt][e] != 0.f) atomicAdd(dw + ((int64_t)k * c_in + ci) * c_out + co, acc[nt][e]);
+        }
+}
+
 // ------------------------------------------------------------------------------------------------
 // weight packing for the tcgen05 paths (training repacks every conv twice per step: forward and data-gradient layout)
 //   src: the parameter, spconv KRSC layout [C_out][K][C_in] fp32
@@ -347,7 +453,7 @@ int tl_bn_relu_bwd(const float* x, const float* d_act, int64_t n, int32_t c, con
 
 int tl_conv_wgrad(const float* src, int64_t src_stride, int32_t c_in, int32_t n_off, const int32_t* index,
                   int64_t index_stride, const uint32_t* tile_mask, const float* d_out, int64_t n_out, int32_t c_out,
-                  float* dw, void* stream_) {
+                  float* dw, int32_t tf32, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     TL_REQUIRE(src && d_out && dw && c_in > 0 && c_out > 0 && n_off >= 1 && n_off <= 27, "tl_conv_wgrad: bad arguments");
     TL_REQUIRE(index || n_off == 1, "tl_conv_wgrad: identity map needs n_off == 1");
@@ -359,8 +465,12 @@ int tl_conv_wgrad(const float* src, int64_t src_stride, int32_t c_in, int32_t n_
     if (target < 1) target = 1;
     const int rpb = train::rows_per_block_for(n_out, target);
     dim3 grid((unsigned)((n_out + rpb - 1) / rpb), (unsigned)n_off, (unsigned)(ci_tiles * co_tiles));
-    train::k_conv_wgrad<<<grid, 64, 0, stream>>>(src, src_stride, c_in, n_off, index, index_stride, tile_mask, d_out,
-                                                 n_out, c_out, rpb, co_tiles, dw);
+    if (tf32)
+        train::k_conv_wgrad_tf32<<<grid, 64, 0, stream>>>(src, src_stride, c_in, n_off, index, index_stride, tile_mask, d_out,
+                                                          n_out, c_out, rpb, co_tiles, dw);
+    else
+        train::k_conv_wgrad<<<grid, 64, 0, stream>>>(src, src_stride, c_in, n_off, index, index_stride, tile_mask, d_out,
+                                                     n_out, c_out, rpb, co_tiles, dw);
     TL_LAUNCH_CHECK();
     return TL_OK;
 }
