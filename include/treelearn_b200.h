@@ -191,6 +191,23 @@ int tl_conv_wgrad(const float* src, int64_t src_stride, int32_t c_in, int32_t n_
                   int64_t index_stride, const uint32_t* tile_mask, const float* d_out, int64_t n_out, int32_t c_out,
                   float* dw, int32_t tf32, void* stream);
 
+/* ---- after the path -----------------------------------------------------------
+ * tl_hash_join_last: exact-coordinate join, replaces the Python `hash(tuple(point))` dictionaries of
+ *      `propagate_preds_hash_vox` (tree_learn/util/pipeline.py:455-465).  Rows are [n,3] fp32 (`*_f64` = 0) or fp64 (1);
+ *      `*_round2` = 1 rounds every coordinate to two decimals first, exactly as numpy.round(x, 2) does in the array's
+ *      dtype (multiply by 100, rint, divide).  Keys compare as fp64 values (-0.0 == 0.0).  out_vals[j] = build_vals of
+ *      the LAST build row whose key equals probe row j (dict(zip(...)) semantics), or `missing`. */
+size_t tl_hash_join_workspace_bytes(int64_t n_build);
+int tl_hash_join_last(const void* build_xyz, int32_t build_f64, int32_t build_round2, const int64_t* build_vals,
+                      int64_t n_build, const void* probe_xyz, int32_t probe_f64, int32_t probe_round2, int64_t n_probe,
+                      int64_t missing, int64_t* out_vals, void* workspace, size_t workspace_bytes, void* stream);
+/* tl_cooccurrence_counts: the point counts behind `get_detections`' IoU / precision / recall matrices
+ *      (tree_learn/util/eval.py:7-31, get_eval_components :230-238).  counts is [(n_pred+1) x (n_gt+1)] u64, overwritten:
+ *      counts[p][g] = #points with pred == p and gt == g; labels outside [0, n) fall into the last row / column, so
+ *      row p sums to |pred == p| and column g to |gt == g|. */
+int tl_cooccurrence_counts(const int64_t* pred, const int64_t* gt, int64_t n, int64_t n_pred, int64_t n_gt,
+                           unsigned long long* counts, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -3,12 +3,12 @@ CPU pre/post-processing helpers (tile generation, hulls, LAS I/O, evaluation, pl
 are out of this build's scope and raise a clear error when touched."""
 from treelearn_b200.pipeline import (assign_remaining_points_nearest_neighbor, ensemble, get_instances,  # noqa: F401
                                       get_pointwise_preds, group_dbscan, group_hdbscan, make_labels_consecutive)
+from treelearn_b200.post import get_detections, propagate_preds, propagate_preds_hash_vox  # noqa: F401
 from treelearn_b200.train_util import (build_dataloader, build_optimizer, checkpoint_save, cuda_cast,  # noqa: F401
                                         is_multiple, load_checkpoint, point_wise_loss)
 
 _OUT_OF_SCOPE = {'generate_tiles', 'get_coords_within_shape', 'get_hull_buffer', 'get_hull', 'get_cluster_means',
-                 'propagate_preds', 'save_treewise', 'load_data', 'save_data', 'propagate_preds_hash_full',
-                 'propagate_preds_hash_vox', 'get_config', 'get_args_and_cfg', 'munch_to_dict', 'get_root_logger',
+                 'save_treewise', 'load_data', 'save_data', 'propagate_preds_hash_full', 'get_config', 'get_args_and_cfg', 'munch_to_dict', 'get_root_logger',
                  'init_train_logger', 'build_cosine_scheduler', 'get_eval_components', 'SampleGenerator'}
 
 

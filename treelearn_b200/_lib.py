@@ -65,6 +65,9 @@ SIGNATURES = {
     'tl_bn_relu_bwd': (C.c_int, [_P, _P, _I64, _I32, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _P]),
     'tl_pack_weight_tc': (C.c_int, [_P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P]),
     'tl_conv_wgrad': (C.c_int, [_P, _I64, _I32, _I32, _P, _I64, _P, _P, _I64, _I32, _P, _I32, _P]),
+    'tl_hash_join_workspace_bytes': (_SZ, [_I64]),
+    'tl_hash_join_last': (C.c_int, [_P, _I32, _I32, _P, _I64, _P, _I32, _I32, _I64, _I64, _P, _P, _SZ, _P]),
+    'tl_cooccurrence_counts': (C.c_int, [_P, _P, _I64, _I64, _I64, _P, _P]),
 }
 
 _lib = None
