@@ -183,7 +183,9 @@ def test_training_step_tf32_default_width_close_to_fp32():
     The tile is tiny, so the deep levels normalise over a handful of voxels and batch-statistics BatchNorm amplifies the
     1e-3 TF32 rounding (and the run-to-run order of the split-K reductions) by two orders of magnitude on individual
     small parameters: the per-parameter bound is therefore loose, the bound on all gradients taken together tight.
-    Per-operator accuracy of the TF32 kernels is pinned by the *_vs_oracle_autograd tests above."""
+    Per-operator accuracy of the TF32 kernels is pinned by the *_vs_oracle_autograd tests above.  Measured on a B200 over
+    repeated runs (profiles/r01_train_tf32_gradient_cosine.txt): all gradients together 0.9998, median parameter 0.994,
+    worst parameter 0.978-0.988 (it moves from run to run)."""
     batch = synth.make_batch([synth.synth_forest(edge=5.0, n_trees=3, seed=3, ground_density=150.0)], inner_edge=3.0)
     sd = model_ref.make_state_dict(channels=32, num_blocks=4, seed=2)
     res = {}
@@ -205,7 +207,7 @@ def test_training_step_tf32_default_width_close_to_fp32():
     ranked = sorted(cos.values())
     print(f'tf32 vs fp32 gradient cosine: all parameters together {total:.5f}, per parameter min {ranked[0]:.5f} '
           f'({worst}), 5th lowest {ranked[4]:.5f}, median {ranked[len(ranked) // 2]:.5f}')
-    assert total > 0.98 and ranked[len(ranked) // 2] > 0.98, (total, ranked[:5])
+    assert total > 0.995 and ranked[len(ranked) // 2] > 0.98, (total, ranked[:5])
 
 
 def test_frozen_modules_and_optimizer_step():
