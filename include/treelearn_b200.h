@@ -208,6 +208,26 @@ int tl_hash_join_last(const void* build_xyz, int32_t build_f64, int32_t build_ro
 int tl_cooccurrence_counts(const int64_t* pred, const int64_t* gt, int64_t n, int64_t n_pred, int64_t n_gt,
                            unsigned long long* counts, void* stream);
 
+/* ---- before the path ------------------------------------------------------------
+ * tl_voxel_downsample_trace: replaces `voxelize` -> open3d 0.17 PointCloud.voxel_down_sample_and_trace
+ *      (tree_learn/util/data_preparation.py:60-79).  points [n,3] fp64 (`round2_first` = numpy.round(points, 2) on the fly,
+ *      :62); voxel index = floor((p - voxel_min_bound) / voxel_size) in fp64 (open3d: voxel_min_bound = min_bound -
+ *      voxel_size / 2).  Per voxel, in ascending (ix, iy, iz) order (open3d's order is std::unordered_map's):
+ *      out_points [m,3] = fp64 sum in input order / count, first_index [m] = lowest input index (the row whose extra
+ *      columns `voxelize` keeps), offsets [m+1] + trace [n] = CSR of the input indices per voxel, in input order.
+ *      out_points / first_index need room for n rows, offsets for n+1.  *n_voxels (host).  Synchronises `stream`. */
+size_t tl_downsample_workspace_bytes(int64_t n_points);
+int tl_voxel_downsample_trace(const double* points, int64_t n_points, int32_t round2_first, double voxel_size,
+                              double voxel_min_bound, double* out_points, int64_t* first_index, int64_t* offsets,
+                              int64_t* trace, int64_t* n_voxels, void* workspace, size_t workspace_bytes, void* stream);
+/* tl_verticality: replaces `compute_features(..., feature_names=['verticality'])` -> jakteristics 0.5.1
+ *      (tree_learn/util/data_preparation.py:83-88).  points [n,3] fp64 -> out [n] fp64: 1 - |n_z| with n the unit
+ *      eigenvector of the smallest eigenvalue of the covariance of all points within `search_radius` (closed ball, the
+ *      point itself included); NaN when fewer than 3 points are in the ball.  Synchronises `stream` once. */
+size_t tl_verticality_workspace_bytes(int64_t n_points);
+int tl_verticality(const double* points, int64_t n_points, double search_radius, double* out, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -4,6 +4,7 @@ are out of this build's scope and raise a clear error when touched."""
 from treelearn_b200.pipeline import (assign_remaining_points_nearest_neighbor, ensemble, get_instances,  # noqa: F401
                                       get_pointwise_preds, group_dbscan, group_hdbscan, make_labels_consecutive)
 from treelearn_b200.post import get_detections, propagate_preds, propagate_preds_hash_vox  # noqa: F401
+from treelearn_b200.prepare import compute_features, voxelize  # noqa: F401
 from treelearn_b200.train_util import (build_dataloader, build_optimizer, checkpoint_save, cuda_cast,  # noqa: F401
                                         is_multiple, load_checkpoint, point_wise_loss)
 

@@ -68,6 +68,10 @@ SIGNATURES = {
     'tl_hash_join_workspace_bytes': (_SZ, [_I64]),
     'tl_hash_join_last': (C.c_int, [_P, _I32, _I32, _P, _I64, _P, _I32, _I32, _I64, _I64, _P, _P, _SZ, _P]),
     'tl_cooccurrence_counts': (C.c_int, [_P, _P, _I64, _I64, _I64, _P, _P]),
+    'tl_downsample_workspace_bytes': (_SZ, [_I64]),
+    'tl_voxel_downsample_trace': (C.c_int, [_P, _I64, _I32, _D, _D, _P, _P, _P, _P, _I64P, _P, _SZ, _P]),
+    'tl_verticality_workspace_bytes': (_SZ, [_I64]),
+    'tl_verticality': (C.c_int, [_P, _I64, _D, _P, _P, _SZ, _P]),
 }
 
 _lib = None
