@@ -30,6 +30,7 @@ def plot_case(seed, edge, shift, inner_edge, outer_edge, stride):
 def main():
     import_reference()
     import tree_learn.util.data_preparation as ref_prep
+    import tree_learn.dataset.dataset as ref_dataset
     assert ref_prep.__file__.startswith('/root/reference')
     logger = logging.getLogger('golden')
     cases = {'a': plot_case(1, 30.0, (120.37, -45.81, 3.0), 8, 13.5, 0.5),          # the configured default edges
@@ -45,6 +46,12 @@ def main():
             gen.tile_generate_and_save(inner_edge, outer_edge, stride, logger=logger)
             files = sorted(os.listdir(os.path.join(tmp, 'tiles', 'npz')), key=lambda s: int(s[:-4].split('_')[-1]))
             tiles = [dict(np.load(os.path.join(tmp, 'tiles', 'npz', f))) for f in files]
+            # the model input the reference's TreeDataset (test mode) + collate_fn build from the first two tiles
+            ds = ref_dataset.TreeDataset(os.path.join(tmp, 'tiles', 'npz'), inner_edge, False, logger)
+            ds.data_paths = [os.path.join(tmp, 'tiles', 'npz', f) for f in files[:2]]
+            batch = ds.collate_fn([ds[0], ds[1]]) if name != 'a' else {}
+            for key, val in batch.items():
+                out[f'{name}:batch:{key}'] = val.numpy() if hasattr(val, 'numpy') else np.asarray(val)
         ora = prepare_ref.cut_tiles_ref(pts, lab, feat, inner_edge, outer_edge, stride)
         assert len(ora) == len(tiles), (name, len(ora), len(tiles))
         for t, (a, b) in enumerate(zip(tiles, ora)):

@@ -160,3 +160,23 @@ def test_prepare_tiles_end_to_end_in_memory():
             assert np.array_equal(a[key], b[key]), key
     inner = sum(int((np.abs(t['points'][:, :2]).max(axis=1) <= 2.0 + 1e-3).sum()) for t in tiles)
     assert inner >= len(plot)                                   # the inner squares (overlapping at stride 0.5) cover the plot
+
+
+# ---- tiles -> model input (treelearn_b200/plot.py), CPU -----------------------------------------------------------------
+@pytest.mark.parametrize('name', ['b', 'c'])
+def test_tiles_to_batches_match_reference_dataset_golden(gold, name):
+    """`tiles_to_batches` against the batch the reference's TreeDataset (test mode) + collate_fn built from the first two
+    golden tiles: same keys, dtypes and values (offset labels, masks, centres, batch ids)."""
+    from treelearn_b200 import plot
+    inner_edge, outer_edge, stride = gold[f'{name}:cfg']
+    tiles = prepare_ref.cut_tiles_ref(gold[f'{name}:points'], gold[f'{name}:labels'], gold[f'{name}:feats'],
+                                      int(inner_edge), float(outer_edge), float(stride))
+    batch = next(plot.tiles_to_batches(tiles[:2], int(inner_edge), batch_size=2))
+    keys = [k.split(':')[-1] for k in gold.files if k.startswith(f'{name}:batch:')]
+    assert sorted(keys) == sorted(batch.keys())
+    for key in keys:
+        want = gold[f'{name}:batch:{key}']
+        got = batch[key].numpy() if torch.is_tensor(batch[key]) else np.asarray(batch[key])
+        assert got.dtype == want.dtype and np.array_equal(got, want), key
+    assert batch['masks_inner'].any() and not batch['masks_inner'].all()
+    assert bool(batch['masks_off'].any()) == (name == 'c')          # case c has a tree inside the first inner squares
