@@ -72,6 +72,37 @@ TS_PRODUCER = r'''    } else if (P.ts && warp < 4 * P.groups) {
         const uint32_t G = (uint32_t)P.groups;
         const uint32_t lane_taddr = tmem_base + ((quarter * 32u) << 16) + (uint32_t)P.a_col0;
         uint32_t my_next = group, c0 = 0, slot = group, phase = 0, witer = 0, nbatch = 0;
+        // One batch of copies is always in flight across batch, fill and work-item boundaries: batch b+1 is issued before
+        // batch b is retired (staging -> registers -> TMEM; the first batch of a fill first waits for the fill slot, the
+        // last one hands the slot to the MMA warp).
+        uint32_t pend_sb = 0, pend_bc = 0, pend_pos = 0, pend_slot = 0, pend_parity = 0;
+        bool pend_last = false;
+        auto retire = [&]() {
+            if (pend_pos == 0) {
+                mbar_wait(L.empty(pend_slot), pend_parity);    // the MMAs that read this fill slot last time have retired
+                tc_fence_after();
+            }
+            for (uint32_t c = 0; c < pend_bc; ++c) {
+                const uint32_t rowaddr = stage0 + (pend_sb * QB + c) * (32u * ROW) + (uint32_t)lane * ROW;
+                const uint32_t taddr = lane_taddr + (pend_slot * Q + pend_pos + c) * COLS;
+#pragma unroll
+                for (int h = 0; h < ROW / 64; ++h) {           // 64 B = 16 columns per store
+                    const uint4 v0 = ld_shared_u4(rowaddr + (((uint32_t)(4 * h + 0) ^ r_swz) << 4));
+                    const uint4 v1 = ld_shared_u4(rowaddr + (((uint32_t)(4 * h + 1) ^ r_swz) << 4));
+                    const uint4 v2 = ld_shared_u4(rowaddr + (((uint32_t)(4 * h + 2) ^ r_swz) << 4));
+                    const uint4 v3 = ld_shared_u4(rowaddr + (((uint32_t)(4 * h + 3) ^ r_swz) << 4));
+                    tmem_st16(taddr + 16 * h, v0, v1, v2, v3);
+                }
+            }
+            if (pend_last) {
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                __syncwarp();
+                if (elect_one()) mbar_arrive(L.full(pend_slot));
+                __syncwarp();
+            }
+            pend_bc = 0;
+        };
         for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++witer) {
             const int tile = w / P.splits;
             const int64_t row0 = (int64_t)tile * BM + quarter * 32;
@@ -113,61 +144,33 @@ TS_PRODUCER = r'''    } else if (P.ts && warp < 4 * P.groups) {
                 }
                 cp_async_commit();
             };
-            // staging buffer sb (chunks [0, bc)) -> TMEM columns of fill slot `slot`, chunk positions [pos, pos + bc)
-            auto transfer_batch = [&](uint32_t sb, uint32_t bc, uint32_t pos) {
-                for (uint32_t c = 0; c < bc; ++c) {
-                    const uint32_t rowaddr = stage0 + (sb * QB + c) * (32u * ROW) + (uint32_t)lane * ROW;
-                    const uint32_t taddr = lane_taddr + (slot * Q + pos + c) * COLS;
-#pragma unroll
-                    for (int h = 0; h < ROW / 64; ++h) {      // 64 B = 16 columns per store
-                        const uint4 v0 = ld_shared_u4(rowaddr + (((uint32_t)(4 * h + 0) ^ r_swz) << 4));
-                        const uint4 v1 = ld_shared_u4(rowaddr + (((uint32_t)(4 * h + 1) ^ r_swz) << 4));
-                        const uint4 v2 = ld_shared_u4(rowaddr + (((uint32_t)(4 * h + 2) ^ r_swz) << 4));
-                        const uint4 v3 = ld_shared_u4(rowaddr + (((uint32_t)(4 * h + 3) ^ r_swz) << 4));
-                        tmem_st16(taddr + 16 * h, v0, v1, v2, v3);
-                    }
-                }
-            };
             while (my_next < c0 + nfill) {
                 const uint32_t j0 = (my_next - c0) * Q;
                 const uint32_t cnt = min(Q, n - j0);
-                bool slot_free = false;
-                uint32_t prev_bc = 0, prev_pos = 0;
                 for (uint32_t b0 = 0; b0 < cnt; b0 += QB) {
                     const uint32_t bc = min(QB, cnt - b0);
                     __syncwarp();                              // every lane is done reading the buffer this batch overwrites
                     issue_batch(j0 + b0, bc, nbatch & 1u);
-                    if (prev_bc) {
+                    if (pend_bc) {                             // the batch issued one step earlier has landed by now (mostly)
                         cp_async_wait<1>();
                         __syncwarp();
-                        if (!slot_free) {
-                            mbar_wait(L.empty(slot), phase ^ 1u);   // the MMAs that read this fill slot last time have retired
-                            tc_fence_after();
-                            slot_free = true;
-                        }
-                        transfer_batch((nbatch & 1u) ^ 1u, prev_bc, prev_pos);
+                        retire();
                     }
-                    prev_bc = bc, prev_pos = b0;
+                    pend_sb = nbatch & 1u, pend_bc = bc, pend_pos = b0, pend_slot = slot, pend_parity = phase ^ 1u;
+                    pend_last = b0 + QB >= cnt;
                     ++nbatch;
                 }
-                cp_async_wait<0>();
-                __syncwarp();
-                if (!slot_free) {
-                    mbar_wait(L.empty(slot), phase ^ 1u);
-                    tc_fence_after();
-                }
-                transfer_batch((nbatch & 1u) ^ 1u, prev_bc, prev_pos);
-                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                tc_fence_before();
-                __syncwarp();
-                if (elect_one()) mbar_arrive(L.full(slot));
-                __syncwarp();
                 my_next += G;
                 slot += G;
                 if (slot >= S) slot -= S, phase ^= 1u;
             }
             c0 += nfill;
-            mbar_arrive(L.wempty(buf));
+            mbar_arrive(L.wempty(buf));       // the item's rulebook rows / chunk list are no longer needed once its copies are issued
+        }
+        if (pend_bc) {
+            cp_async_wait<0>();
+            __syncwarp();
+            retire();
         }
     } else if (!P.ts && warp < P.q * P.groups) {'''
 
