@@ -25,6 +25,18 @@ def test_library_exports_every_declared_symbol():
     assert lib.tl_version() >= 1
 
 
+def test_ctypes_signatures_have_the_declared_argument_counts():
+    """Guards the hand-written ctypes table against drifting from the header (an extra / missing argument is silent in C)."""
+    header = open(os.path.join(ROOT, 'include', 'treelearn_b200.h')).read()
+    header = re.sub(r'/\*.*?\*/', '', header, flags=re.S)
+    decls = dict(re.findall(r'\b(tl_[a-z0-9_]+)\s*\(([^)]*)\)\s*;', header))
+    assert set(decls) == set(_lib.SIGNATURES)
+    for name, params in decls.items():
+        params = params.strip()
+        count = 0 if params in ('', 'void') else params.count(',') + 1
+        assert count == len(_lib.SIGNATURES[name][1]), (name, count, len(_lib.SIGNATURES[name][1]))
+
+
 def test_state_dict_layout_matches_reference():
     g = np.load(os.path.join(ROOT, 'tests', 'golden', 'model_small.npz'))
     keys = [k[3:] for k in g.files if k.startswith('sd:')]
