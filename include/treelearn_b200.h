@@ -89,7 +89,8 @@ typedef struct {
     int32_t n_out;
     int32_t c_out;
     int32_t n_seg;
-    int32_t reserved;
+    int32_t src_fp32_mask; /* modes 2/3: bit s set = segment s reads raw fp32 rows [*, c_in] (the residual stream) and
+                              converts them to the operand format in registers; 0 = every source is in the operand format */
     tl_conv_seg seg[TL_MAX_SEG];
     const float* residual; /* [n_out, c_out] or NULL */
     float* out_raw;
@@ -106,12 +107,19 @@ typedef struct {
 #define TL_MODE_TF32 1
 #define TL_MODE_F16 2 /* tcgen05 kind::f16: segment sources, weights and the activated outputs (out_act1/2) are fp16;
                          residual, out_raw and the accumulation stay fp32 */
+#define TL_MODE_F16X2 3 /* two-term fp16 split of both operands (x = hi + lo, three tcgen05.mma per K step, fp32 accumulate):
+                           products carry ~22 mantissa bits = the reference's fp32 arithmetic (tree_learn inference runs spconv
+                           in fp32: configs/pipeline/pipeline.yaml:12 `fp16` is never read).  Segment sources and activated
+                           outputs are [row][C/32][2][32] fp16 (per 32-channel block: 64 B of hi halves, 64 B of lo halves);
+                           weights [n_off][c_in/32][2][c_out][32] fp16.  Modes 2 and 3 take the K order inside a 32-channel
+                           block permuted (treelearn_b200/sparse.py::pack_weight_ts). */
 int tl_conv_fwd(const tl_conv_desc* desc, int32_t mode, void* stream);
 
 /* ---- voxel -> point gather + the two MLP heads: replaces `features[v2p_map]` and MLP forward
  *      (tree_learn/model/tree_learn.py:97-103, blocks.py:8-18).  BN(eval) is folded into w1/b1 by the host.
  * voxel_feats [M,C]; v2p [N]; per head h in {sem(2), off(3)}: w1 [C][C] (row = out), b1 [C], w2 [O][C], b2 [O]. */
-int tl_heads_fwd(const void* voxel_feats, int32_t feats_half /* 1: voxel_feats is fp16 (TL_MODE_F16 backbone) */,
+int tl_heads_fwd(const void* voxel_feats, int32_t feats_half /* 0: fp32 rows; 1: fp16 rows (TL_MODE_F16 backbone); 2: the
+                 TL_MODE_F16X2 operand format [M][C/32][2][32] fp16 */,
                  const int64_t* v2p, int64_t n_points, int32_t channels,
                  const float* sem_w1, const float* sem_b1, const float* sem_w2, const float* sem_b2,
                  const float* off_w1, const float* off_b1, const float* off_w2, const float* off_b2,

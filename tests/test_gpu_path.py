@@ -355,7 +355,8 @@ def test_f16_subm_conv_parity(ci, co):
     res = torch.randn((lv.n, co), generator=g)
     s, t = torch.rand(co, generator=g) + 0.5, torch.randn(co, generator=g)
     ref = model_ref._subm(x.float(), sp.subm_neighbour_table(vc.cpu().numpy(), [500, 500, 1000]), w.float()) + res
-    wp = sparse.pack_weight_tc(w.reshape(co, 27, ci).permute(1, 0, 2).cuda(), True)
+    wk = w.reshape(co, 27, ci).permute(1, 0, 2).cuda()
+    wp = sparse.pack_weight_ts(wk.float(), 1) if sparse.USE_TS else sparse.pack_weight_tc(wk, True)
     raw, act = sparse.conv([sparse.Seg(x.cuda(), wp, lv.nbr, lv.nbr_mask)], lv.n, co, _lib.MODE_F16,
                            residual=res.cuda(), raw=True, act1=(s.cuda(), t.cuda()))
     assert raw.dtype == torch.float32 and act.dtype == torch.float16

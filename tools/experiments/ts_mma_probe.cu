@@ -70,6 +70,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 constexpr int kACol = 256;      // TMEM column of the TS form's A operand
 
 // mode 0: A from shared memory (SS), mode 1: A from TMEM (TS).  cycles[mode] = clock64 ticks for reps*chunks*2 MMAs + commit.
+template <int MODE>
 __global__ void __launch_bounds__(128) k_probe(const __half* __restrict__ A, const __half* __restrict__ B, int n, int chunks,
                                                int reps, float* __restrict__ d_ss, float* __restrict__ d_ts,
                                                long long* __restrict__ cycles) {
@@ -116,26 +117,47 @@ __global__ void __launch_bounds__(128) k_probe(const __half* __restrict__ A, con
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t idesc = idesc_f16(n), barrier = smem_u32(&bar);
     uint32_t parity = 0;
-    for (int mode = 0; mode < 2; ++mode) {
+    {
+        constexpr int mode = MODE;
         long long t0 = 0;
-        if (tid == 0) {
+        if (warp == 0) {
+          uint32_t el = 0;
+          asm volatile("{\n.reg .b32 rx;\n.reg .pred px;\nelect.sync rx|px, 0xffffffff;\nselp.u32 %0, 1, 0, px;\n}\n" : "=r"(el)::"memory");
+          if (el) {
             t0 = clock64();
-            for (int rep = 0; rep < reps; ++rep)
-                for (int c = 0; c < chunks; ++c) {
-                    const uint64_t ad = smem_desc_sw64(smem_u32(a_s + (size_t)c * 128 * 64));
-                    const uint64_t bd = smem_desc_sw64(smem_u32(b_s + (size_t)c * n * 64));
+            const uint64_t ad0 = smem_desc_sw64(smem_u32(a_s)), bd0 = smem_desc_sw64(smem_u32(b_s));
+            const uint32_t a_step = (128 * 64) >> 4, b_step = (uint32_t)(n * 64) >> 4;
+            if (chunks == 8) {   // lean issue loop: constant strides, fully unrolled over the 8 chunks
+                for (int rep = 0; rep < reps; ++rep) {
 #pragma unroll
-                    for (int kk = 0; kk < 2; ++kk) {
-                        const uint32_t acc = (rep | c | kk) != 0;
-                        if (mode == 0) mma_ss(tmem, ad + 2 * kk, bd + 2 * kk, idesc, acc);
-                        else mma_ts(tmem, tmem + kACol + 16 * c + 8 * kk, bd + 2 * kk, idesc, acc);
+                    for (int c = 0; c < 8; ++c) {
+#pragma unroll
+                        for (int kk = 0; kk < 2; ++kk) {
+                            const uint32_t acc = (rep | c | kk) != 0;
+                            if (mode == 0) mma_ss(tmem, ad0 + (uint64_t)(c * a_step + 2 * kk), bd0 + (uint64_t)(c * b_step + 2 * kk), idesc, acc);
+                            else mma_ts(tmem, tmem + kACol + 16 * c + 8 * kk, bd0 + (uint64_t)(c * b_step + 2 * kk), idesc, acc);
+                        }
                     }
                 }
+            } else {
+                for (int rep = 0; rep < reps; ++rep)
+                    for (int c = 0; c < chunks; ++c) {
+                        const uint64_t ad = ad0 + (uint64_t)(c * a_step), bd = bd0 + (uint64_t)(c * b_step);
+#pragma unroll
+                        for (int kk = 0; kk < 2; ++kk) {
+                            const uint32_t acc = (rep | c | kk) != 0;
+                            if (mode == 0) mma_ss(tmem, ad + 2 * kk, bd + 2 * kk, idesc, acc);
+                            else mma_ts(tmem, tmem + kACol + 16 * c + 8 * kk, bd + 2 * kk, idesc, acc);
+                        }
+                    }
+            }
             commit(barrier);
+          }
+          __syncwarp();
         }
         mbar_wait(barrier, parity);
         parity ^= 1;
-        if (tid == 0) cycles[mode] = clock64() - t0;
+        if (warp == 0 && t0) cycles[mode] = clock64() - t0;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         float* out = mode == 0 ? d_ss : d_ts;                  // row 32*warp + lane, 16 columns at a time
         for (int col = 0; col < n; col += 16) {
@@ -158,8 +180,9 @@ extern "C" int ts_mma_probe(const void* A, const void* B, int n, int chunks, int
                             long long* cycles, void* stream) {
     if (n < 16 || n > 256 || n % 16 || chunks < 1 || chunks > 12 || reps < 1) return -1;
     const size_t smem = (size_t)chunks * (128 + n) * 64;
-    cudaError_t e = cudaFuncSetAttribute(k_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return -2;
-    k_probe<<<1, 128, smem, (cudaStream_t)stream>>>((const __half*)A, (const __half*)B, n, chunks, reps, d_ss, d_ts, cycles);
+    cudaFuncSetAttribute(k_probe<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_probe<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_probe<0><<<1, 128, smem, (cudaStream_t)stream>>>((const __half*)A, (const __half*)B, n, chunks, reps, d_ss, d_ts, cycles);
+    k_probe<1><<<1, 128, smem, (cudaStream_t)stream>>>((const __half*)A, (const __half*)B, n, chunks, reps, d_ss, d_ts, cycles);
     return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }

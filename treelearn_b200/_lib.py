@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, 'libtreelearn_b200.so')
 
 TL_MAX_SEG = 3
 TILE_ROWS = 128
-MODE_FP32, MODE_TF32, MODE_F16 = 0, 1, 2
+MODE_FP32, MODE_TF32, MODE_F16, MODE_F16X2 = 0, 1, 2, 3
 ERR_REACH_ZERO = -3
 
 
@@ -25,7 +25,7 @@ class ConvSeg(C.Structure):
 
 
 class ConvDesc(C.Structure):
-    _fields_ = [('n_out', C.c_int32), ('c_out', C.c_int32), ('n_seg', C.c_int32), ('reserved', C.c_int32),
+    _fields_ = [('n_out', C.c_int32), ('c_out', C.c_int32), ('n_seg', C.c_int32), ('src_fp32_mask', C.c_int32),
                 ('seg', ConvSeg * TL_MAX_SEG), ('residual', C.c_void_p), ('out_raw', C.c_void_p),
                 ('out_act1', C.c_void_p), ('scale1', C.c_void_p), ('shift1', C.c_void_p),
                 ('out_act2', C.c_void_p), ('scale2', C.c_void_p), ('shift2', C.c_void_p), ('splitk_ws', C.c_void_p)]

@@ -22,11 +22,11 @@
 #include <stdlib.h>
 
 #include "tl_common.cuh"
+#include "tl_tc_ptx.cuh"
 
 namespace tl {
 namespace tc {
 
-constexpr int BM = 128;          // rows per tile == TMEM lanes
 constexpr int BK = 32;           // channels per K block: one swizzle row of 128 B (fp32/TF32 operands) or 64 B (fp16)
 constexpr int MAX_STAGES = 12;
 constexpr int kProducerWarps = 12;       // gather warps: groups of q warps, group g fills the ring slots with ordinal % G == g
@@ -47,188 +47,6 @@ constexpr int SEGTAB_BYTES = 32 * TL_MAX_SEG;
 // reads do not serialise on one L2 line (a single shared zero row made the kernel 8x slower).
 __device__ float g_zero_rows[256 * 256];
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(bar),
-        "r"(parity)
-        : "memory");
-}
-// per-tile waits (descriptor / accumulator hand-offs) back off between polls so that they do not steal issue slots
-// from the gather warps (measured: 20 % of all issued instructions were try_wait spins)
-__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, uint32_t ns) {
-    uint32_t done = 0;
-    while (true) {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (done) break;
-        if (ns) __nanosleep(ns);
-    }
-}
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async16_cg(uint32_t dst, const void* src, uint32_t src_bytes) {   // L2 only
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ int ld_shared_i32(uint32_t addr) {
-    int v;
-    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
-}
-// the mbarrier is arrived on (without bumping its pending count) once all prior cp.async of this thread completed
-__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
-//   [0,14) start address >> 4 | [16,30) LBO >> 4 (ignored for swizzled K-major, set 1) | [32,46) SBO >> 4 (8 rows
-//   x 128 B = 1024) | [46,48) version = 1 (sm100) | [49,52) base offset = 0 (1024 B aligned stages) |
-//   [61,64) layout = 2 (SWIZZLE_128B)
-// row_bytes 128 -> SWIZZLE_128B (layout 2, SBO 1024); row_bytes 64 -> SWIZZLE_64B (layout 4, SBO 512)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, int row_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)((8 * row_bytes) >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)(row_bytes == 128 ? 2 : 4) << 61;
-    return d;
-}
-// cute::UMMA::InstrDescriptor: c_format F32 (1) @4, a/b format TF32 (2) @7/@10, K-major both, N>>3 @17, M>>4 @24
-__device__ __forceinline__ uint32_t make_idesc(int n, bool half) {   // a/b format: 2 = TF32, 0 = F16
-    const uint32_t fmt = half ? 0u : 2u;
-    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                         uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// accumulate-always forms (enable_input_d = true folds to the constant predicate: no setp / predicate moves per MMA)
-__device__ __forceinline__ void umma_tf32_acc(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.eq.u32 p, 1, 1;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc)
-        : "memory");
-}
-__device__ __forceinline__ void umma_f16_acc(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.eq.u32 p, 1, 1;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ float round_tf32(float v) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-    return __uint_as_float(r);
-}
-
-// 4 consecutive activated columns -> the consumer's operand format (16 B of TF32-rounded fp32 or 8 B of fp16)
-template <int EB>
-__device__ __forceinline__ void store_act4(void* out, int64_t e, float a0, float a1, float a2, float a3) {
-    if (EB == 4) {
-        *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + e) =
-            make_float4(round_tf32(a0), round_tf32(a1), round_tf32(a2), round_tf32(a3));
-    } else {
-        const __half2 h0 = __floats2half2_rn(a0, a1), h1 = __floats2half2_rn(a2, a3);
-        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(out) + e) =
-            make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
-    }
-}
-template <int EB>
-__device__ __forceinline__ void store_act1(void* out, int64_t e, float a) {
-    if (EB == 4) reinterpret_cast<float*>(out)[e] = round_tf32(a);
-    else reinterpret_cast<__half*>(out)[e] = __float2half_rn(a);
-}
-
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-// TMA bulk copy global -> shared, completion (bytes) signalled on the mbarrier
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ uint2 ld_shared_u2(uint32_t addr) {
-    uint2 v;
-    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
-    return v;
-}
-
 // ---- optional timeline trace (TL_TC_DEBUG bit 32): CTA 0 records clock64() at the ring hand-offs of its first fills so that
 // the slot round trip can be split into issue / data latency / MMA / barrier hops (tools/trace_conv.py)
 constexpr int TRACE_ROLES = 8, TRACE_LEN = 2048;
@@ -246,21 +64,6 @@ __device__ __forceinline__ void trace(bool on, int role, uint32_t& pos, uint32_t
     }
 }
 
-// one lane of a converged warp (cute::elect_one_sync): keeps the surrounding loop warp-uniform, so the compiler holds
-// descriptors / barrier addresses in uniform registers instead of wrapping every tcgen05 / bulk-copy instruction in a
-// per-lane "waterfall" loop (measured: ~375 issue cycles per chunk in the old `if (lane == 0)` MMA loop)
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred = 0;
-    asm volatile(
-        "{\n"
-        ".reg .b32 rx;\n"
-        ".reg .pred px;\n"
-        "elect.sync rx|px, 0xffffffff;\n"
-        "selp.u32 %0, 1, 0, px;\n"
-        "}\n"
-        : "=r"(pred)::"memory");
-    return pred != 0;
-}
 
 struct Launch {   // per-launch scalars (kernel parameter)
     int num_tiles;     // row tiles
@@ -684,12 +487,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const tl_conv_desc d, c
                         if (d.out_act1) {
                             const float a0 = fmaxf(fmaf(v.x, s1.x, t1.x), 0.f), a1 = fmaxf(fmaf(v.y, s1.y, t1.y), 0.f);
                             const float a2 = fmaxf(fmaf(v.z, s1.z, t1.z), 0.f), a3 = fmaxf(fmaf(v.w, s1.w, t1.w), 0.f);
-                            store_act4<EB>(d.out_act1, o, a0, a1, a2, a3);
+                            store_act4<EB>(d.out_act1, grow, N, col, a0, a1, a2, a3);
                         }
                         if (d.out_act2) {
                             const float a0 = fmaxf(fmaf(v.x, s2.x, t2.x), 0.f), a1 = fmaxf(fmaf(v.y, s2.y, t2.y), 0.f);
                             const float a2 = fmaxf(fmaf(v.z, s2.z, t2.z), 0.f), a3 = fmaxf(fmaf(v.w, s2.w, t2.w), 0.f);
-                            store_act4<EB>(d.out_act2, o, a0, a1, a2, a3);
+                            store_act4<EB>(d.out_act2, grow, N, col, a0, a1, a2, a3);
                         }
                     }
                     __syncwarp();
@@ -788,8 +591,8 @@ __global__ void k_splitk_epilogue(const tl_conv_desc d, const float* __restrict_
         float v = ws[e];
         if (d.residual) v += __ldg(d.residual + e);
         if (d.out_raw) d.out_raw[e] = v;
-        if (d.out_act1) store_act1<EB>(d.out_act1, e, fmaxf(fmaf(v, __ldg(d.scale1 + col), __ldg(d.shift1 + col)), 0.f));
-        if (d.out_act2) store_act1<EB>(d.out_act2, e, fmaxf(fmaf(v, __ldg(d.scale2 + col), __ldg(d.shift2 + col)), 0.f));
+        if (d.out_act1) store_act1<EB>(d.out_act1, e, d.c_out, fmaxf(fmaf(v, __ldg(d.scale1 + col), __ldg(d.shift1 + col)), 0.f));
+        if (d.out_act2) store_act1<EB>(d.out_act2, e, d.c_out, fmaxf(fmaf(v, __ldg(d.scale2 + col), __ldg(d.shift2 + col)), 0.f));
     }
 }
 
@@ -863,10 +666,10 @@ __global__ void __launch_bounds__(128) k_conv_in4(const tl_conv_desc d) {
         }
         if (d.out_raw) *reinterpret_cast<float4*>(d.out_raw + o) = v;
         if (d.out_act1)
-            store_act4<EB>(d.out_act1, o, fmaxf(fmaf(v.x, s1.x, t1.x), 0.f), fmaxf(fmaf(v.y, s1.y, t1.y), 0.f),
+            store_act4<EB>(d.out_act1, grow, 32, col, fmaxf(fmaf(v.x, s1.x, t1.x), 0.f), fmaxf(fmaf(v.y, s1.y, t1.y), 0.f),
                            fmaxf(fmaf(v.z, s1.z, t1.z), 0.f), fmaxf(fmaf(v.w, s1.w, t1.w), 0.f));
         if (d.out_act2)
-            store_act4<EB>(d.out_act2, o, fmaxf(fmaf(v.x, s2.x, t2.x), 0.f), fmaxf(fmaf(v.y, s2.y, t2.y), 0.f),
+            store_act4<EB>(d.out_act2, grow, 32, col, fmaxf(fmaf(v.x, s2.x, t2.x), 0.f), fmaxf(fmaf(v.y, s2.y, t2.y), 0.f),
                            fmaxf(fmaf(v.z, s2.z, t2.z), 0.f), fmaxf(fmaf(v.w, s2.w, t2.w), 0.f));
     }
 }
@@ -893,14 +696,19 @@ static int conv_fwd_simt_fallback_note(const tl_conv_desc&, cudaStream_t) {
     return TL_ERR_UNSUPPORTED;
 }
 
+// the 4-channel network input is always fp32; only the activated output follows the operand format `fmt` (tc::FMT_*)
+int conv_fwd_in4(const tl_conv_desc& d, cudaStream_t stream, int fmt) {
+    const unsigned grid = (unsigned)((d.n_out + 127) / 128);
+    if (fmt == tc::FMT_F16) tc::k_conv_in4<tc::FMT_F16><<<grid, 128, 0, stream>>>(d);
+    else if (fmt == tc::FMT_F16X2) tc::k_conv_in4<tc::FMT_F16X2><<<grid, 128, 0, stream>>>(d);
+    else tc::k_conv_in4<tc::FMT_TF32><<<grid, 128, 0, stream>>>(d);
+    TL_LAUNCH_CHECK();
+    return TL_OK;
+}
+
 int conv_fwd_tc(const tl_conv_desc& d, cudaStream_t stream, bool half) {
-    if (d.n_seg == 1 && d.seg[0].c_in == 4 && d.c_out == 32 && d.seg[0].index && d.seg[0].src_stride == 4) {
-        // the 4-channel network input is always fp32; only the activated output follows the operand format
-        if (half) tc::k_conv_in4<2><<<(unsigned)((d.n_out + 127) / 128), 128, 0, stream>>>(d);
-        else tc::k_conv_in4<4><<<(unsigned)((d.n_out + 127) / 128), 128, 0, stream>>>(d);
-        TL_LAUNCH_CHECK();
-        return TL_OK;
-    }
+    if (d.n_seg == 1 && d.seg[0].c_in == 4 && d.c_out == 32 && d.seg[0].index && d.seg[0].src_stride == 4)
+        return conv_fwd_in4(d, stream, half ? tc::FMT_F16 : tc::FMT_TF32);
     if (!tc_eligible(d)) {
         if (half) {
             set_error("tl_conv_fwd(f16): shape not eligible for the tcgen05 path (c_in %% 32, c_out %% 32, c_out <= 256)");

@@ -78,9 +78,13 @@ class TreeLearn(nn.Module):
         self.use_feats, self.use_coords = use_feats, use_coords
         self.spatial_shape = spatial_shape
         self.max_num_points_per_voxel = max_num_points_per_voxel
-        self.mode = mode                      # 'fp32' (SIMT, exact-ish), 'tf32' or 'f16' (tcgen05; f16 = fp16 operands)
-        if mode == 'f16' and channels % 32 != 0:
-            raise ValueError("mode='f16' needs channels % 32 == 0 (every conv must take the tcgen05 path)")
+        # 'fp32' (SIMT, exact-ish) | 'tf32' | 'f16' (tcgen05, fp16 operands) | 'f16x2' (tcgen05, two-term fp16 split of both
+        # operands = fp32-equivalent products: the reference's inference arithmetic is fp32)
+        self.mode = mode
+        if mode not in ('fp32', 'tf32', 'f16', 'f16x2'):
+            raise ValueError(f'unknown mode {mode!r}')
+        if mode in ('f16', 'f16x2') and channels % 32 != 0:
+            raise ValueError(f"mode={mode!r} needs channels % 32 == 0 (every conv must take the tcgen05 path)")
         self.planes = [channels * (i + 1) for i in range(num_blocks)]
         self._norm = functools.partial(nn.BatchNorm1d, eps=BN_EPS, momentum=BN_MOMENTUM)
         self._packed = None
@@ -158,6 +162,7 @@ class TreeLearn(nn.Module):
             return self._packed
         tf32 = self.mode in ('tf32', 'f16')
         half = self.mode == 'f16'
+        ts = 2 if self.mode == 'f16x2' else (1 if (half and sparse.USE_TS) else 0)   # tensor-memory-A kernel: (hi, lo) terms
         pk = {'key': key}
         with torch.no_grad():
             for name, m in self.named_modules():
@@ -172,7 +177,9 @@ class TreeLearn(nn.Module):
                         pieces = [w]
                     out = []
                     for piece in pieces:
-                        if half and tc_eligible(piece.shape[2], co) and 'i_branch' not in name:
+                        if ts and tc_eligible(piece.shape[2], co):
+                            out.append(sparse.pack_weight_ts(piece.permute(1, 0, 2), ts))      # TMEM-A kernel: B slabs (+ lo terms)
+                        elif half and tc_eligible(piece.shape[2], co) and 'i_branch' not in name:
                             out.append(sparse.pack_weight_tc(piece.permute(1, 0, 2), True))    # fp16 B-operand slabs
                         elif tf32 and tc_eligible(piece.shape[2], co):
                             out.append(sparse.pack_weight_tc(piece.permute(1, 0, 2), False))   # TF32 B-operand slabs
@@ -274,7 +281,7 @@ class TreeLearn(nn.Module):
 
     def _run_backbone(self, vfeats, levels):
         pk = self._pack()
-        mode = {'fp32': _lib.MODE_FP32, 'tf32': _lib.MODE_TF32, 'f16': _lib.MODE_F16}[self.mode]
+        mode = {'fp32': _lib.MODE_FP32, 'tf32': _lib.MODE_TF32, 'f16': _lib.MODE_F16, 'f16x2': _lib.MODE_F16X2}[self.mode]
         g0 = levels[0]
         x, xa = sparse.conv([Seg(vfeats, pk['input_conv.0'][0], g0.nbr, g0.nbr_mask)], g0.n, self.planes[0], mode,
                             raw=True, act1=pk['unet.blocks.block0.conv_branch.0'])
@@ -302,7 +309,7 @@ class TreeLearn(nn.Module):
         e, ea = conv([Seg(ua, pk[p + '.deconv.2'][0], g.up_index, g.up_mask)], raw=True, act1=(s_cat[c:], t_cat[c:]))
         wa, wi = pk[t0 + '.conv_branch.2'], pk[t0 + '.i_branch.0']
         ha = conv([nbr(za_tail, wa[0]), nbr(ea, wa[1])], act1=pk[t0 + '.conv_branch.3'])
-        if mode == _lib.MODE_F16:
+        if mode == _lib.MODE_F16 and not sparse.USE_TS:
             # the 1x1 projection reads the fp32 residual-stream tensors: run it as its own TF32 launch and feed it in
             # as the residual of the fp16-operand 3^3 conv
             proj = sparse.conv([Seg(z, wi[0]), Seg(e, wi[1])], n, c, _lib.MODE_TF32, raw=True)
@@ -319,7 +326,7 @@ class TreeLearn(nn.Module):
             feats = voxel_out.float()[v2p]
             return {'backbone_feats': feats, 'semantic_prediction_logits': self.semantic_linear(feats),
                     'offset_predictions': self.offset_linear(feats)}
-        feats, logits, offs = sparse.heads(voxel_out, v2p, self._pack())
+        feats, logits, offs = sparse.heads(voxel_out, v2p, self._pack(), split=self.mode == 'f16x2')
         return {'backbone_feats': feats, 'semantic_prediction_logits': logits, 'offset_predictions': offs}
 
     def get_loss(self, model_output, semantic_labels, offset_labels, masks_off, masks_sem, **kwargs):

@@ -12,7 +12,8 @@ files, LAS output.
 import numpy as np
 import torch
 
-from . import pipeline, post, prepare
+from . import dataset, pipeline, post, prepare
+from .dataset import offset_labels  # noqa: F401  (kept under its old name)
 
 # tree_learn/dataset/dataset.py:7-10 and tree_learn/util/pipeline.py (grouping labels)
 INSTANCE_LABEL_IGNORE_IN_RAW_DATA = -1
@@ -24,53 +25,16 @@ NOT_ASSIGNED_LABEL_IN_GROUPING = -1
 START_NUM_PREDS = 1
 
 
-def offset_labels(xyz, instance_label, semantic_label):
-    """Per-point vector to the tree base = mean of the points within 0.5 m above the (regularised) lowest point of the
-    instance (`TreeDataset.getOffset`, dataset.py:121-150).  Returns (offsets f32 [n,3], valid mask)."""
-    position = np.ones_like(xyz, dtype=np.float32)
-    valid = np.zeros(len(instance_label), dtype=bool)
-    for inst in np.unique(instance_label):
-        idx = np.where(instance_label == inst)[0]
-        if semantic_label[idx[0]] == NON_TREE_CLASS_IN_PYTORCH_DATASET:
-            continue
-        z = xyz[idx, 2]
-        low = np.partition(z, 10)[3] if len(z) > 11 else z.min()
-        near_base = xyz[idx][z <= low + 0.5]
-        if len(near_base) > 0:
-            position[idx] = np.mean(near_base, axis=0)
-            valid[idx] = True
-        else:
-            position[idx] = np.array([0, 0, 0])
-    return position - xyz, valid
-
-
 def tile_sample(tile, inner_square_edge_length):
     """One tile dict of `prepare.cut_tiles` -> the tensors `TreeDataset.__getitem__` returns in test mode."""
-    xyz, inst = tile['points'], tile['instance_label']
-    sem = np.where(inst == NON_TREE_CLASS_IN_RAW_DATA, NON_TREE_CLASS_IN_PYTORCH_DATASET,
-                   TREE_CLASS_IN_PYTORCH_DATASET).astype(np.float64)
-    center = np.ones_like(xyz) * tile['center']
-    off, off_valid = offset_labels(xyz, inst, sem)
-    inner = np.linalg.norm(xyz[:, :-1], ord=np.inf, axis=1) <= (inner_square_edge_length / 2)
-    keep = inst != INSTANCE_LABEL_IGNORE_IN_RAW_DATA
-    return dict(coords=torch.from_numpy(xyz), input_feats=torch.from_numpy(tile['feat']),
-                instance_labels=torch.from_numpy(inst), semantic_labels=torch.from_numpy(sem),
-                offset_labels=torch.from_numpy(off), centers=torch.from_numpy(center),
-                masks_inner=torch.from_numpy(inner), masks_sem=torch.from_numpy(inner & keep),
-                masks_off=torch.from_numpy(inner & keep & (sem != NON_TREE_CLASS_IN_PYTORCH_DATASET) & off_valid))
+    return dataset.sample_from_arrays(tile['points'], tile['feat'], tile['instance_label'], tile['center'],
+                                      inner_square_edge_length)
 
 
 def tiles_to_batches(tiles, inner_square_edge_length, batch_size=1):
     """Generator of model input dicts (`TreeDataset.collate_fn`, dataset.py:176-226) over the tiles, in order."""
-    as_type = dict(coords=torch.float32, input_feats=torch.float32, semantic_labels=torch.long, instance_labels=torch.long,
-                   masks_inner=torch.bool, masks_off=torch.bool, masks_sem=torch.bool, offset_labels=torch.float32,
-                   centers=torch.float32)
     for start in range(0, len(tiles), batch_size):
-        samples = [tile_sample(t, inner_square_edge_length) for t in tiles[start:start + batch_size]]
-        batch = {k: torch.cat([s[k] for s in samples], 0).to(dt) for k, dt in as_type.items()}
-        batch['batch_ids'] = torch.cat([torch.full((len(s['coords']),), b, dtype=torch.long) for b, s in enumerate(samples)])
-        batch['batch_size'] = len(samples)
-        yield batch
+        yield dataset.collate_samples([tile_sample(t, inner_square_edge_length) for t in tiles[start:start + batch_size]])
 
 
 def segment_points(model, data, model_cfg, grouping_cfg, voxel_size=0.1, search_radius_features=0.6, inner_edge=8,

@@ -213,6 +213,50 @@ def pack_weight_tc(w, half, bk=None):
     return t.reshape(k, ci // bk, co, bk).contiguous()
 
 
+USE_TS = os.environ.get('TL_TS', '1') != '0'   # f16 convs: A operand in tensor memory (csrc/tl_conv_ts.cu); 0 = round-1 kernel
+
+
+def pack_weight_ts(w, nsplit=1):
+    """w [n_off, C_out, C_in] -> the B-operand image of the tensor-memory-A kernel (csrc/tl_conv_ts.cu):
+    [n_off, C_in/32, nsplit, C_out, 32] fp16, one contiguous slab per (offset, 32-channel block).
+    * K order inside a block is permuted: K step kk (16 positions), position 4q+e holds channel 8q + 4kk + e -- what a
+      quad of lanes reading one contiguous 64 B row piece delivers through the tcgen05.st.16x256b fragment layout;
+    * every 64 B row carries the UMMA SWIZZLE_64B image (16 B chunk c of row n at c ^ ((n >> 1) & 3));
+    * nsplit = 2 (mode f16x2): a (hi, lo) pair of slabs with hi = fp16(w), lo = fp16(w - hi)."""
+    k, co, ci = w.shape
+    assert ci % 32 == 0 and co % 32 == 0, (ci, co)
+    w = w.detach().float()
+    hi = w.half()
+    parts = [hi] if nsplit == 1 else [hi, (w - hi.float()).half()]
+    dev = w.device
+    pos = torch.arange(32, device=dev)
+    kk, kap = pos // 16, pos % 16
+    chan = 8 * (kap // 4) + 4 * kk + kap % 4                       # channel held by K position `pos`
+    n = torch.arange(co, device=dev)
+    src_chunk = torch.arange(4, device=dev)[None, :] ^ ((n >> 1) & 3)[:, None]   # destination chunk c holds source chunk c ^ x
+    out = []
+    for t in parts:
+        t = t.reshape(k, co, ci // 32, 32)[..., chan]              # permuted K order
+        t = t.permute(0, 2, 1, 3).reshape(k, ci // 32, co, 4, 8)   # [k, kb, co, chunk, 8 halves]
+        t = torch.gather(t, 3, src_chunk[None, None, :, :, None].expand(k, ci // 32, co, 4, 8))
+        out.append(t.reshape(k, ci // 32, co, 32))
+    return torch.stack(out, 2).contiguous()                        # [k, kb, nsplit, co, 32]
+
+
+def to_split(x):
+    """fp32 [rows, C] -> the f16x2 operand format [rows, C/32, 2, 32] fp16 (returned as [rows, 2C])."""
+    r, c = x.shape
+    hi = x.half()
+    lo = (x - hi.float()).half()
+    return torch.stack([hi.reshape(r, c // 32, 32), lo.reshape(r, c // 32, 32)], 2).reshape(r, 2 * c).contiguous()
+
+
+def from_split(x):
+    r, c2 = x.shape
+    v = x.reshape(r, c2 // 64, 2, 32).float()
+    return (v[:, :, 0] + v[:, :, 1]).reshape(r, c2 // 2)
+
+
 SPLITK_MAX_ROWS = 2 * 148 * TILE_ROWS   # below two waves of 128-row tiles the library may split K over CTAs
 PROFILE = None   # bench.py sets this to a list: every conv launch appends (start_evt, end_evt, alg_bytes, flops)
 
@@ -224,25 +268,31 @@ def conv(segs, n_out, c_out, mode, residual=None, raw=False, act1=None, act2=Non
     dev = segs[0].src.device
     d = _lib.ConvDesc()
     d.n_out, d.c_out, d.n_seg = int(n_out), int(c_out), len(segs)
+    half_modes = (_lib.MODE_F16, _lib.MODE_F16X2)
     for i, s in enumerate(segs):
         g = d.seg[i]
         g.src, g.src_stride, g.c_in = ptr(s.src), s.src.stride(0), s.src.shape[1]
+        if mode in half_modes and s.src.dtype == torch.float32:
+            d.src_fp32_mask |= 1 << i          # raw residual-stream rows, converted to the operand format in registers
+        elif mode == _lib.MODE_F16X2:          # [rows, C/32, 2, 32] fp16 stored as [rows, 2C]
+            g.src_stride, g.c_in = s.src.stride(0) // 2, s.src.shape[1] // 2
         g.weight, g.n_off = ptr(s.weight), s.weight.shape[0]
         if s.index is not None:
             g.index, g.index_stride, g.tile_mask = ptr(s.index), s.index.stride(0), ptr(s.mask)
     outs = []
     d.residual = ptr(residual)
-    act_dtype = torch.float16 if mode == _lib.MODE_F16 else torch.float32   # operand format of the consumers
+    act_dtype = torch.float16 if mode in half_modes else torch.float32   # operand format of the consumers
+    act_cols = 2 * c_out if mode == _lib.MODE_F16X2 else c_out            # f16x2: (hi, lo) halves per channel
     if raw:
         o = torch.empty((n_out, c_out), dtype=torch.float32, device=dev)
         d.out_raw = ptr(o)
         outs.append(o)
     if act1 is not None:
-        o = torch.empty((n_out, c_out), dtype=act_dtype, device=dev)
+        o = torch.empty((n_out, act_cols), dtype=act_dtype, device=dev)
         d.out_act1, d.scale1, d.shift1 = ptr(o), ptr(act1[0]), ptr(act1[1])
         outs.append(o)
     if act2 is not None:
-        o = torch.empty((n_out, c_out), dtype=act_dtype, device=dev)
+        o = torch.empty((n_out, act_cols), dtype=act_dtype, device=dev)
         d.out_act2, d.scale2, d.shift2 = ptr(o), ptr(act2[0]), ptr(act2[1])
         outs.append(o)
     if mode != _lib.MODE_FP32 and 0 < n_out < SPLITK_MAX_ROWS:
@@ -250,6 +300,8 @@ def conv(segs, n_out, c_out, mode, residual=None, raw=False, act1=None, act2=Non
         d.splitk_ws = ptr(ws)
     if PROFILE is not None and n_out > 0:
         # algorithmic traffic: every input row once + one output + index tables + weights
+        # ONE output per conv in the element size of the stream it feeds (extra activated copies, the residual
+        # read and BN/ReLU count as fused = 0 bytes); f16x2 activations are 4 B per channel (hi + lo)
         byts = n_out * c_out * (2 if (mode == _lib.MODE_F16 and not raw) else 4)
         flops = 0
         for s in segs:
@@ -267,16 +319,18 @@ def conv(segs, n_out, c_out, mode, residual=None, raw=False, act1=None, act2=Non
     return outs[0] if len(outs) == 1 else tuple(outs)
 
 
-def heads(voxel_feats, v2p, packed):
-    """voxel->point gather + both 2-layer heads (tree_learn.py:97-103).  packed: dict of folded weights."""
+def heads(voxel_feats, v2p, packed, split=False):
+    """voxel->point gather + both 2-layer heads (tree_learn.py:97-103).  packed: dict of folded weights.
+    voxel_feats: fp32 [M,C], fp16 [M,C], or (split=True) the f16x2 operand format [M,2C]."""
     lib = _lib.load()
     n = int(v2p.shape[0])
-    c = int(voxel_feats.shape[1])
+    c = int(voxel_feats.shape[1]) // (2 if split else 1)
     dev = voxel_feats.device
     feats = torch.empty((n, c), dtype=torch.float32, device=dev)
     logits = torch.empty((n, 2), dtype=torch.float32, device=dev)
     offs = torch.empty((n, 3), dtype=torch.float32, device=dev)
-    check(lib.tl_heads_fwd(ptr(voxel_feats), int(voxel_feats.dtype == torch.float16), ptr(v2p), n, c, ptr(packed['sem_w1']), ptr(packed['sem_b1']),
+    fmt = 0 if voxel_feats.dtype == torch.float32 else (2 if split else 1)
+    check(lib.tl_heads_fwd(ptr(voxel_feats), fmt, ptr(v2p), n, c, ptr(packed['sem_w1']), ptr(packed['sem_b1']),
                            ptr(packed['sem_w2']), ptr(packed['sem_b2']), ptr(packed['off_w1']), ptr(packed['off_b1']),
                            ptr(packed['off_w2']), ptr(packed['off_b2']), ptr(feats), ptr(logits), ptr(offs),
                            stream_ptr()))

@@ -23,7 +23,7 @@ def cuda_cast(func):
     return wrapper
 
 
-def checkpoint_save(epoch, model, optimizer, work_dir, save_freq=16):
+def checkpoint_save(epoch, model, optimizer, work_dir, save_freq=1):
     """Write epoch_{n}.pth = {net (cpu), optimizer, epoch}; drop epoch_{n-1}.pth unless n-1 is a multiple of save_freq."""
     net = model.module if hasattr(model, 'module') else model
     state = {'net': {k: v.cpu() for k, v in net.state_dict().items()}, 'optimizer': optimizer.state_dict(), 'epoch': epoch}
@@ -61,7 +61,8 @@ def build_optimizer(model, optim_cfg):
     return getattr(torch.optim, kind)(filter(lambda p: p.requires_grad, model.parameters()), **cfg)
 
 
-def build_dataloader(dataset, training, dist=False, **kwargs):
-    sampler = torch.utils.data.distributed.DistributedSampler(dataset, shuffle=training) if dist else None
-    return DataLoader(dataset, collate_fn=dataset.collate_fn, shuffle=(training and sampler is None), sampler=sampler,
-                      drop_last=training, pin_memory=True, **kwargs)
+def build_dataloader(dataset, batch_size=1, num_workers=1, training=True, dist=False):
+    """Reference util/train.py:125-141: a DistributedSampler only for `dist and training`; shuffle / drop_last in training."""
+    sampler = torch.utils.data.distributed.DistributedSampler(dataset, shuffle=True) if (dist and training) else None
+    return DataLoader(dataset, batch_size=batch_size, num_workers=num_workers, collate_fn=dataset.collate_fn,
+                      shuffle=(training and sampler is None), sampler=sampler, drop_last=training, pin_memory=True)
