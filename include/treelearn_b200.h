@@ -111,15 +111,19 @@ typedef struct {
                            products carry ~22 mantissa bits = the reference's fp32 arithmetic (tree_learn inference runs spconv
                            in fp32: configs/pipeline/pipeline.yaml:12 `fp16` is never read).  Segment sources and activated
                            outputs are [row][C/32][2][32] fp16 (per 32-channel block: 64 B of hi halves, 64 B of lo halves);
-                           weights [n_off][c_in/32][2][c_out][32] fp16.  Modes 2 and 3 take the K order inside a 32-channel
-                           block permuted (treelearn_b200/sparse.py::pack_weight_ts). */
+                           weights [n_off][c_in/32][2][c_out][32] fp16.
+                           The tensor-memory-A kernel behind modes 2 and 3 (csrc/tl_conv_ts.cu) keeps every tensor it reads or
+                           writes -- fp32 residual / raw output, activated operands -- in "P-layout": inside each 32-channel
+                           block, position 8q + 2g + e holds logical channel 8g + 2q + e (q, g = 0..3, e = 0..1); the weights
+                           carry the matching K order (treelearn_b200/sparse.py: PI, to_p / from_p, pack_weight_ts).  scale /
+                           shift stay in logical order.  TL_TS=0 selects round 1's shared-memory-A kernel (natural layout). */
 int tl_conv_fwd(const tl_conv_desc* desc, int32_t mode, void* stream);
 
 /* ---- voxel -> point gather + the two MLP heads: replaces `features[v2p_map]` and MLP forward
  *      (tree_learn/model/tree_learn.py:97-103, blocks.py:8-18).  BN(eval) is folded into w1/b1 by the host.
  * voxel_feats [M,C]; v2p [N]; per head h in {sem(2), off(3)}: w1 [C][C] (row = out), b1 [C], w2 [O][C], b2 [O]. */
-int tl_heads_fwd(const void* voxel_feats, int32_t feats_half /* 0: fp32 rows; 1: fp16 rows (TL_MODE_F16 backbone); 2: the
-                 TL_MODE_F16X2 operand format [M][C/32][2][32] fp16 */,
+int tl_heads_fwd(const void* voxel_feats, int32_t feats_half /* 0: fp32 rows; 1: fp16 rows; 2: the TL_MODE_F16X2 operand format
+                 [M][C/32][2][32] fp16 in P-layout; 3: fp16 rows in P-layout (TL_MODE_F16 backbone, tensor-memory-A kernel) */,
                  const int64_t* v2p, int64_t n_points, int32_t channels,
                  const float* sem_w1, const float* sem_b1, const float* sem_w2, const float* sem_b2,
                  const float* off_w1, const float* off_b1, const float* off_w2, const float* off_b2,

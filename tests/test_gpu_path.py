@@ -356,10 +356,12 @@ def test_f16_subm_conv_parity(ci, co):
     s, t = torch.rand(co, generator=g) + 0.5, torch.randn(co, generator=g)
     ref = model_ref._subm(x.float(), sp.subm_neighbour_table(vc.cpu().numpy(), [500, 500, 1000]), w.float()) + res
     wk = w.reshape(co, 27, ci).permute(1, 0, 2).cuda()
-    wp = sparse.pack_weight_ts(wk.float(), 1) if sparse.USE_TS else sparse.pack_weight_tc(wk, True)
-    raw, act = sparse.conv([sparse.Seg(x.cuda(), wp, lv.nbr, lv.nbr_mask)], lv.n, co, _lib.MODE_F16,
-                           residual=res.cuda(), raw=True, act1=(s.cuda(), t.cuda()))
+    wp = sparse.pack_weight(wk.float(), 1) if sparse.USE_TS else sparse.pack_weight_tc(wk, True)
+    to_k, from_k = (sparse.to_p, sparse.from_p) if sparse.USE_TS else ((lambda a: a), (lambda a: a))   # kernel layout
+    raw, act = sparse.conv([sparse.Seg(to_k(x.cuda()), wp, lv.nbr, lv.nbr_mask)], lv.n, co, _lib.MODE_F16,
+                           residual=to_k(res.cuda()), raw=True, act1=(s.cuda(), t.cuda()))
     assert raw.dtype == torch.float32 and act.dtype == torch.float16
+    raw, act = from_k(raw), from_k(act)
     assert torch.allclose(raw.cpu(), ref, **TF32_EXACT_TOL)
     assert torch.allclose(act.cpu().float(), torch.relu(ref * s + t), atol=3e-3, rtol=2e-3)   # + fp16 rounding of the store
 

@@ -1,0 +1,70 @@
+"""Timeline of k_conv_ts on SM 0 (TRACE build, TL_TS_DEBUG bit 32) for one submanifold conv of the cfg2 tile.
+    make -C treelearn_b200/csrc TRACE=1
+    TL_LIB=treelearn_b200/libtreelearn_b200_trace.so TL_TS_DEBUG=32 python tools/trace_ts.py [32|64|96|128] [f16|f16x2]
+Events (tag = tile ordinal << 3 | event) of the four warps of group 0 on CTA 0 (roles 0..3):
+  0 tile begins, 1 main loop done, 2 accumulator complete, 3 epilogue done"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from treelearn_b200 import _lib, sparse, synth  # noqa: E402
+
+assert int(os.environ.get('TL_TS_DEBUG', '0')) & 32, 'run with TL_TS_DEBUG=32 and the TRACE build (TL_LIB=...)'
+c_ch = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+mode = sys.argv[2] if len(sys.argv) > 2 else 'f16'
+nsplit = 2 if mode == 'f16x2' else 1
+level = {32: 0, 64: 1, 96: 2, 128: 3}[c_ch]
+batch = synth.make_batch([synth.workload('cfg2_2M')])
+dev = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in batch.items()}
+vf, vc, keys, v2p = sparse.voxelize(dev['coords'], dev['input_feats'], dev['batch_ids'], 1, 0.1, False, False, 3)
+lv = sparse.build_levels(keys, vc, [1000, 1000, 1000], level + 1)[level]
+g = torch.Generator(device='cuda').manual_seed(0)
+x = torch.randn((lv.n, c_ch), device='cuda', generator=g)
+x = sparse.to_split(x) if nsplit == 2 else x.half()
+w = sparse.pack_weight_ts(torch.randn((27, c_ch, c_ch), device='cuda', generator=g) / 30, nsplit)
+s, t = torch.ones(c_ch, device='cuda'), torch.zeros(c_ch, device='cuda')
+m = _lib.MODE_F16X2 if nsplit == 2 else _lib.MODE_F16
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+for _ in range(3):
+    e0.record()
+    out = sparse.conv([sparse.Seg(x, w, lv.nbr, lv.nbr_mask)], lv.n, c_ch, m, act1=(s, t))
+    e1.record()
+torch.cuda.synchronize()
+tiles = (lv.n + 127) // 128
+print(f'level {level}: {lv.n} voxels, {tiles} tiles ({tiles / 148:.1f} per SM), C = {c_ch}, mode {mode}: {e0.elapsed_time(e1) * 1e3:.1f} us')
+lib = C.CDLL(_lib.LIB_PATH)
+ROLES, LEN = 8, 4096
+buf = np.zeros(ROLES * LEN, dtype=np.uint64)
+assert lib.tl_debug_copy_trace_ts(C.c_void_p(buf.ctypes.data), C.c_size_t(buf.nbytes)) == 0
+buf = buf.reshape(ROLES, LEN)
+tag, clk = (buf >> np.uint64(48)).astype(np.int64), (buf & np.uint64((1 << 48) - 1)).astype(np.int64)
+ev = {}
+for role in range(ROLES):
+    for p in range(LEN):
+        if buf[role, p] == 0:
+            break
+        ev[(role, int(tag[role, p]) >> 3, int(tag[role, p]) & 7)] = int(clk[role, p])
+
+
+def stat(name, vals):
+    a = np.array(vals, dtype=np.float64)
+    if len(a):
+        print(f'{name:58s} median {np.median(a):7.0f}  mean {a.mean():7.0f}  p90 {np.percentile(a, 90):7.0f}  n {len(a)}')
+
+
+# roles 0..3 = the four warps (TMEM lane quarters) of group 0 on CTA 0; per round (= tile): 0 begin, 1 main loop done,
+# 2 accumulator complete seen, 3 epilogue done
+rounds = sorted({r for (role, r, e) in ev if role == 0 and e == 3})
+print(f'traced: {len(rounds)} tiles of group 0 on SM 0')
+R_ = rounds[1:-1]
+for w in range(4):
+    stat(f'warp {w}: main loop (gather -> TMEM -> MMA issue)', [ev[(w, r, 1)] - ev[(w, r, 0)] for r in R_ if (w, r, 1) in ev])
+    stat(f'warp {w}: next-tile index staging + wait for accumulator', [ev[(w, r, 2)] - ev[(w, r, 1)] for r in R_ if (w, r, 2) in ev])
+    stat(f'warp {w}: epilogue', [ev[(w, r, 3)] - ev[(w, r, 2)] for r in R_ if (w, r, 3) in ev])
+    stat(f'warp {w}: epilogue done -> next tile begins', [ev[(w, r + 1, 0)] - ev[(w, r, 3)] for r in R_ if (w, r + 1, 0) in ev])
+if len(R_) > 2:
+    print(f'group 0: {(ev[(0, R_[-1], 3)] - ev[(0, R_[0], 3)]) / (len(R_) - 1):.0f} cycles per tile in steady state')

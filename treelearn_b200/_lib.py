@@ -10,7 +10,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libtreelearn_b200.so')
+LIB_PATH = os.environ.get('TL_LIB') or os.path.join(_HERE, 'libtreelearn_b200.so')   # TL_LIB: e.g. the TRACE=1 build
 
 TL_MAX_SEG = 3
 TILE_ROWS = 128

@@ -7,6 +7,7 @@
 #include <stdlib.h>
 
 #include "tl_common.cuh"
+#include "tl_tc_ptx.cuh"
 
 namespace tl {
 
@@ -124,14 +125,16 @@ int conv_fwd_simt(const tl_conv_desc& d, cudaStream_t stream) {
 }
 
 int conv_fwd_tc(const tl_conv_desc& d, cudaStream_t stream, bool half);  // tl_conv_tc.cu
-int conv_fwd_in4(const tl_conv_desc& d, cudaStream_t stream, int fmt);   // tl_conv_tc.cu
+int conv_fwd_in4(const tl_conv_desc& d, cudaStream_t stream, int fmt, bool perm);   // tl_conv_tc.cu
 bool conv_ts_eligible(const tl_conv_desc& d);                            // tl_conv_ts.cu
 int conv_fwd_ts(const tl_conv_desc& d, cudaStream_t stream, int nsplit, uint32_t src_fp32_mask);
+bool conv_grp_eligible(const tl_conv_desc& d, uint32_t src_fp32_mask);   // tl_conv_grp.cu
+int conv_fwd_grp(const tl_conv_desc& d, cudaStream_t stream, int nsplit);
 
 // ------------------------------------------------------------------------------------------------
 // voxel -> point gather + both MLP heads, one thread per point, weights broadcast from smem
 // ------------------------------------------------------------------------------------------------
-template <int C, int FMT>   // FMT: 0 fp32 rows, 1 fp16 rows, 2 f16x2 operand format ([C/32][2][32] fp16: hi + lo)
+template <int C, int FMT>   // FMT: 0 fp32 rows, 1 fp16 rows, 2 f16x2 operand format ([C/32][2][32] fp16: hi + lo, P-layout), 3 fp16 rows in P-layout
 __global__ void __launch_bounds__(128) k_heads(const void* __restrict__ vfeat_, const int64_t* __restrict__ v2p,
                                                int64_t n, const float* __restrict__ sw1, const float* __restrict__ sb1,
                                                const float* __restrict__ sw2, const float* __restrict__ sb2,
@@ -171,9 +174,25 @@ __global__ void __launch_bounds__(128) k_heads(const void* __restrict__ vfeat_, 
             const uint2 rh = __ldg(src + blk * 16 + j / 4), rl = __ldg(src + blk * 16 + 8 + j / 4);
             const float2 h0 = __half22float2(*reinterpret_cast<const __half2*>(&rh.x)), h1 = __half22float2(*reinterpret_cast<const __half2*>(&rh.y));
             const float2 l0 = __half22float2(*reinterpret_cast<const __half2*>(&rl.x)), l1 = __half22float2(*reinterpret_cast<const __half2*>(&rl.y));
-            x[4 * c] = h0.x + l0.x, x[4 * c + 1] = h0.y + l0.y, x[4 * c + 2] = h1.x + l1.x, x[4 * c + 3] = h1.y + l1.y;
-            dst[c] = make_float4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
+            // positions 4c .. 4c+3 of the P-layout row -> logical channels
+            x[blk * 32 + tc::p_chan(j)] = h0.x + l0.x, x[blk * 32 + tc::p_chan(j + 1)] = h0.y + l0.y;
+            x[blk * 32 + tc::p_chan(j + 2)] = h1.x + l1.x, x[blk * 32 + tc::p_chan(j + 3)] = h1.y + l1.y;
         }
+#pragma unroll
+        for (int c = 0; c < C / 4; ++c) dst[c] = make_float4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
+    } else if (FMT == 3) {
+        const uint2* src = reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(vfeat_) + v2p[i] * C);
+#pragma unroll
+        for (int c = 0; c < C / 4; ++c) {
+            const int blk = (4 * c) / 32, j = (4 * c) % 32;
+            const uint2 raw = __ldg(src + c);
+            const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+            const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+            x[blk * 32 + tc::p_chan(j)] = lo.x, x[blk * 32 + tc::p_chan(j + 1)] = lo.y;
+            x[blk * 32 + tc::p_chan(j + 2)] = hi.x, x[blk * 32 + tc::p_chan(j + 3)] = hi.y;
+        }
+#pragma unroll
+        for (int c = 0; c < C / 4; ++c) dst[c] = make_float4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
     } else if (FMT == 1) {
         const uint2* src = reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(vfeat_) + v2p[i] * C);
 #pragma unroll
@@ -256,14 +275,19 @@ int tl_conv_fwd(const tl_conv_desc* desc, int32_t mode, void* stream_) {
     const bool in4 = d.n_seg == 1 && d.seg[0].c_in == 4 && d.c_out == 32 && d.seg[0].index && d.seg[0].src_stride == 4;
     if (mode == TL_MODE_F16) {
         // A operand in tensor memory (tl_conv_ts.cu) unless TL_TS=0 asks for the shared-memory form of round 1
+        // TL_TS: 1 (default) group kernel, cp.async gather + shared-memory-A MMA (tl_conv_grp.cu); 2 tensor-memory-A kernel
+        // (tl_conv_ts.cu); 0 round 1's kernel (natural channel order)
         static const int use_ts = getenv("TL_TS") ? atoi(getenv("TL_TS")) : 1;
-        if (in4) return conv_fwd_in4(d, stream, 2);      // the 4-channel network input is always fp32
+        if (in4) return conv_fwd_in4(d, stream, 2, use_ts != 0);      // the 4-channel network input is always fp32
+        if (use_ts == 1 && conv_grp_eligible(d, (uint32_t)d.src_fp32_mask)) return conv_fwd_grp(d, stream, 1);
         if (use_ts && conv_ts_eligible(d)) return conv_fwd_ts(d, stream, 1, (uint32_t)d.src_fp32_mask);
         TL_REQUIRE(d.src_fp32_mask == 0, "tl_conv_fwd(f16): fp32 segment sources need the tensor-memory path");
         return conv_fwd_tc(d, stream, true);
     }
     if (mode == TL_MODE_F16X2) {
-        if (in4) return conv_fwd_in4(d, stream, 22);
+        static const int use_ts2 = getenv("TL_TS") ? atoi(getenv("TL_TS")) : 1;
+        if (in4) return conv_fwd_in4(d, stream, 22, true);
+        if (use_ts2 == 1 && conv_grp_eligible(d, (uint32_t)d.src_fp32_mask)) return conv_fwd_grp(d, stream, 2);
         if (!conv_ts_eligible(d)) {
             set_error("tl_conv_fwd(f16x2): shape not eligible (c_in %% 32, c_out %% 32, <= 256 channels)");
             return TL_ERR_UNSUPPORTED;
@@ -280,12 +304,15 @@ int tl_heads_fwd(const void* voxel_feats, int32_t feats_half, const int64_t* v2p
                  float* sem_logits, float* offsets, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (n == 0) return TL_OK;
-    TL_REQUIRE(feats_half >= 0 && feats_half <= 2 && (feats_half != 2 || channels % 32 == 0),
+    TL_REQUIRE(feats_half >= 0 && feats_half <= 3 && (feats_half < 2 || channels % 32 == 0),
                "tl_heads_fwd: feats format %d with %d channels", feats_half, channels);
     const unsigned grid = (unsigned)((n + 127) / 128);
 #define TL_HEADS(C)                                                                                                 \
     if (feats_half == 2 && C % 32 == 0)                                                                             \
         k_heads<C, (C % 32 == 0 ? 2 : 0)><<<grid, 128, 0, stream>>>(voxel_feats, v2p, n, sem_w1, sem_b1, sem_w2, sem_b2, off_w1, \
+                                                 off_b1, off_w2, off_b2, backbone_feats, sem_logits, offsets);      \
+    else if (feats_half == 3 && C % 32 == 0)                                                                        \
+        k_heads<C, (C % 32 == 0 ? 3 : 0)><<<grid, 128, 0, stream>>>(voxel_feats, v2p, n, sem_w1, sem_b1, sem_w2, sem_b2, off_w1, \
                                                  off_b1, off_w2, off_b2, backbone_feats, sem_logits, offsets);      \
     else if (feats_half == 1)                                                                                       \
         k_heads<C, 1><<<grid, 128, 0, stream>>>(voxel_feats, v2p, n, sem_w1, sem_b1, sem_w2, sem_b2, off_w1,        \

@@ -600,7 +600,8 @@ __global__ void k_splitk_epilogue(const tl_conv_desc d, const float* __restrict_
 // 4-channel input convolution (tree_learn.py:37-39): K = 4 is below one UMMA K block, so it runs as SIMT:
 // one thread per voxel, 27 gathered float4 rows, weights [27][4][32] broadcast from shared memory.
 // ------------------------------------------------------------------------------------------------
-template <int EB>
+// PERM: outputs in the P-layout of the tensor-memory-A kernel (position m of the 32-channel row = logical channel p_chan(m))
+template <int EB, bool PERM>
 __global__ void __launch_bounds__(128) k_conv_in4(const tl_conv_desc d) {
     __shared__ __align__(16) float ws[27 * 4 * 32];
     __shared__ __align__(16) float stage[4][32 * 32];     // per warp: 32 rows x 32 columns, transposed for coalesced stores
@@ -645,14 +646,19 @@ __global__ void __launch_bounds__(128) k_conv_in4(const tl_conv_desc d) {
     // row `lane` -> shared (16 B chunk j at j ^ (lane & 7)), then every store instruction covers whole 128 B lines
     float* st = stage[warp];
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
+    for (int j = 0; j < 8; ++j)     // positions 4j .. 4j+3 of the row
         *reinterpret_cast<float4*>(st + lane * 32 + ((j ^ (lane & 7)) << 2)) =
-            make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+            PERM ? make_float4(acc[p_chan(4 * j)], acc[p_chan(4 * j + 1)], acc[p_chan(4 * j + 2)], acc[p_chan(4 * j + 3)])
+                 : make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
     __syncwarp();
     const int cc = lane & 7, rsub = lane >> 3, col = 4 * cc;
     float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), t1 = s1, s2 = s1, t2 = s1;
-    if (d.out_act1) s1 = __ldg(reinterpret_cast<const float4*>(d.scale1 + col)), t1 = __ldg(reinterpret_cast<const float4*>(d.shift1 + col));
-    if (d.out_act2) s2 = __ldg(reinterpret_cast<const float4*>(d.scale2 + col)), t2 = __ldg(reinterpret_cast<const float4*>(d.shift2 + col));
+    auto vec4 = [&](const float* p) {   // scale / shift (logical order) of the 4 channels stored at positions col .. col+3
+        return PERM ? make_float4(__ldg(p + p_chan(col)), __ldg(p + p_chan(col + 1)), __ldg(p + p_chan(col + 2)), __ldg(p + p_chan(col + 3)))
+                    : __ldg(reinterpret_cast<const float4*>(p + col));
+    };
+    if (d.out_act1) s1 = vec4(d.scale1), t1 = vec4(d.shift1);
+    if (d.out_act2) s2 = vec4(d.scale2), t2 = vec4(d.shift2);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int rr = i * 4 + rsub;
@@ -696,19 +702,21 @@ static int conv_fwd_simt_fallback_note(const tl_conv_desc&, cudaStream_t) {
     return TL_ERR_UNSUPPORTED;
 }
 
-// the 4-channel network input is always fp32; only the activated output follows the operand format `fmt` (tc::FMT_*)
-int conv_fwd_in4(const tl_conv_desc& d, cudaStream_t stream, int fmt) {
+// the 4-channel network input is always fp32; the outputs follow the operand format `fmt` (tc::FMT_*) and, with `perm`,
+// the P-layout of the tensor-memory-A kernel (raw fp32 output included)
+int conv_fwd_in4(const tl_conv_desc& d, cudaStream_t stream, int fmt, bool perm) {
     const unsigned grid = (unsigned)((d.n_out + 127) / 128);
-    if (fmt == tc::FMT_F16) tc::k_conv_in4<tc::FMT_F16><<<grid, 128, 0, stream>>>(d);
-    else if (fmt == tc::FMT_F16X2) tc::k_conv_in4<tc::FMT_F16X2><<<grid, 128, 0, stream>>>(d);
-    else tc::k_conv_in4<tc::FMT_TF32><<<grid, 128, 0, stream>>>(d);
+    if (fmt == tc::FMT_F16 && perm) tc::k_conv_in4<tc::FMT_F16, true><<<grid, 128, 0, stream>>>(d);
+    else if (fmt == tc::FMT_F16) tc::k_conv_in4<tc::FMT_F16, false><<<grid, 128, 0, stream>>>(d);
+    else if (fmt == tc::FMT_F16X2) tc::k_conv_in4<tc::FMT_F16X2, true><<<grid, 128, 0, stream>>>(d);
+    else tc::k_conv_in4<tc::FMT_TF32, false><<<grid, 128, 0, stream>>>(d);
     TL_LAUNCH_CHECK();
     return TL_OK;
 }
 
 int conv_fwd_tc(const tl_conv_desc& d, cudaStream_t stream, bool half) {
     if (d.n_seg == 1 && d.seg[0].c_in == 4 && d.c_out == 32 && d.seg[0].index && d.seg[0].src_stride == 4)
-        return conv_fwd_in4(d, stream, half ? tc::FMT_F16 : tc::FMT_TF32);
+        return conv_fwd_in4(d, stream, half ? tc::FMT_F16 : tc::FMT_TF32, false);
     if (!tc_eligible(d)) {
         if (half) {
             set_error("tl_conv_fwd(f16): shape not eligible for the tcgen05 path (c_in %% 32, c_out %% 32, c_out <= 256)");

@@ -167,6 +167,8 @@ __device__ __forceinline__ void split_half2(float a, float b, uint32_t& hi, uint
 //   FMT_F16X2 [row][C/32][2][32] fp16: per 32-channel block 64 B of hi halves, then 64 B of lo halves (TL_MODE_F16X2);
 //             a gathered 32-channel row piece stays one contiguous 128 B line
 constexpr int FMT_TF32 = 4, FMT_F16 = 2, FMT_F16X2 = 22;
+// P-layout of the tensor-memory-A kernel (tl_conv_ts.cu): logical channel stored at position m of a 32-channel block
+__host__ __device__ constexpr int p_chan(int m) { return 8 * ((m % 8) / 2) + 2 * (m / 8) + (m % 2); }
 
 // 4 consecutive activated columns (col % 4 == 0) of one row -> the consumer's operand format
 template <int FMT>

@@ -177,8 +177,14 @@ class TreeLearn(nn.Module):
                         pieces = [w]
                     out = []
                     for piece in pieces:
-                        if ts and tc_eligible(piece.shape[2], co):
-                            out.append(sparse.pack_weight_ts(piece.permute(1, 0, 2), ts))      # TMEM-A kernel: B slabs (+ lo terms)
+                        if ts and 'i_branch' in name and sparse.TS_KIND == 1:
+                            # 1x1 projection of the fp32 residual stream (P-layout in and out): fp32 SIMT kernel in mode
+                            # f16x2 (exact), round 1's TF32 kernel in mode f16; natural addressing, so both channel axes
+                            # of the weight are permuted instead
+                            wp = sparse.permute_p_weight(piece.permute(1, 0, 2))
+                            out.append(wp.permute(0, 2, 1).contiguous() if ts == 2 else sparse.pack_weight_tc(wp, False))
+                        elif ts and tc_eligible(piece.shape[2], co):
+                            out.append(sparse.pack_weight(piece.permute(1, 0, 2), ts))      # f16 / f16x2 kernels: B slabs (+ lo terms)
                         elif half and tc_eligible(piece.shape[2], co) and 'i_branch' not in name:
                             out.append(sparse.pack_weight_tc(piece.permute(1, 0, 2), True))    # fp16 B-operand slabs
                         elif tf32 and tc_eligible(piece.shape[2], co):
@@ -309,10 +315,11 @@ class TreeLearn(nn.Module):
         e, ea = conv([Seg(ua, pk[p + '.deconv.2'][0], g.up_index, g.up_mask)], raw=True, act1=(s_cat[c:], t_cat[c:]))
         wa, wi = pk[t0 + '.conv_branch.2'], pk[t0 + '.i_branch.0']
         ha = conv([nbr(za_tail, wa[0]), nbr(ea, wa[1])], act1=pk[t0 + '.conv_branch.3'])
-        if mode == _lib.MODE_F16 and not sparse.USE_TS:
-            # the 1x1 projection reads the fp32 residual-stream tensors: run it as its own TF32 launch and feed it in
-            # as the residual of the fp16-operand 3^3 conv
-            proj = sparse.conv([Seg(z, wi[0]), Seg(e, wi[1])], n, c, _lib.MODE_TF32, raw=True)
+        if mode in (_lib.MODE_F16, _lib.MODE_F16X2) and sparse.TS_KIND != 2:
+            # the 1x1 projection reads the fp32 residual-stream tensors: run it as its own launch (TF32 tensor cores in mode
+            # f16, fp32 FMA in mode f16x2) and feed it in as the residual of the fp16-operand 3^3 conv
+            pmode = _lib.MODE_FP32 if (mode == _lib.MODE_F16X2) else _lib.MODE_TF32
+            proj = sparse.conv([Seg(z, wi[0]), Seg(e, wi[1])], n, c, pmode, raw=True)
             t, ta = conv([nbr(ha, pk[t0 + '.conv_branch.5'][0])], residual=proj, raw=True, act1=pk[t1 + '.0'])
         else:
             t, ta = conv([nbr(ha, pk[t0 + '.conv_branch.5'][0]), Seg(z, wi[0]), Seg(e, wi[1])], raw=True,

@@ -213,14 +213,35 @@ def pack_weight_tc(w, half, bk=None):
     return t.reshape(k, ci // bk, co, bk).contiguous()
 
 
-USE_TS = os.environ.get('TL_TS', '1') != '0'   # f16 convs: A operand in tensor memory (csrc/tl_conv_ts.cu); 0 = round-1 kernel
+# TL_TS: 1 (default) group kernel csrc/tl_conv_grp.cu; 2 tensor-memory-A kernel csrc/tl_conv_ts.cu; 0 round-1 kernel (natural layout)
+TS_KIND = int(os.environ.get('TL_TS', '1'))
+USE_TS = TS_KIND != 0
+
+
+# ---- "P-layout" of the tensor-memory-A kernel (csrc/tl_conv_ts.cu) -----------------------------------------------------
+# Within every 32-channel block, position m = 8q + 2g + e of a row holds logical channel 8g + 2q + e (q, g in 0..3,
+# e in 0..1): PI[m] = logical channel stored at position m.  Used by the fp32 residual stream and the activated operand
+# tensors of modes f16 / f16x2; scale / shift vectors and the model's inputs / outputs stay in logical order.
+PI = [8 * ((m % 8) // 2) + 2 * (m // 8) + (m % 2) for m in range(32)]
+PI_INV = [PI.index(c) for c in range(32)]
+
+
+def to_p(x):
+    """[rows, C] logical channel order -> P-layout (C % 32 == 0)."""
+    r, c = x.shape
+    return x.reshape(r, c // 32, 32)[:, :, torch.tensor(PI, device=x.device)].reshape(r, c).contiguous()
+
+
+def from_p(x):
+    r, c = x.shape
+    return x.reshape(r, c // 32, 32)[:, :, torch.tensor(PI_INV, device=x.device)].reshape(r, c).contiguous()
 
 
 def pack_weight_ts(w, nsplit=1):
-    """w [n_off, C_out, C_in] -> the B-operand image of the tensor-memory-A kernel (csrc/tl_conv_ts.cu):
+    """w [n_off, C_out, C_in] (logical channels) -> the B-operand image of the tensor-memory-A kernel:
     [n_off, C_in/32, nsplit, C_out, 32] fp16, one contiguous slab per (offset, 32-channel block).
-    * K order inside a block is permuted: K step kk (16 positions), position 4q+e holds channel 8q + 4kk + e -- what a
-      quad of lanes reading one contiguous 64 B row piece delivers through the tcgen05.st.16x256b fragment layout;
+    * K order inside a block: K step kk, position 4q + j is what lane q of a quad delivers from bytes [8kk, 8kk + 8) of its
+      16 B piece of a P-layout row, i.e. memory position 8q + 4kk + j = logical channel PI[8q + 4kk + j];
     * every 64 B row carries the UMMA SWIZZLE_64B image (16 B chunk c of row n at c ^ ((n >> 1) & 3));
     * nsplit = 2 (mode f16x2): a (hi, lo) pair of slabs with hi = fp16(w), lo = fp16(w - hi)."""
     k, co, ci = w.shape
@@ -229,22 +250,58 @@ def pack_weight_ts(w, nsplit=1):
     hi = w.half()
     parts = [hi] if nsplit == 1 else [hi, (w - hi.float()).half()]
     dev = w.device
-    pos = torch.arange(32, device=dev)
-    kk, kap = pos // 16, pos % 16
-    chan = 8 * (kap // 4) + 4 * kk + kap % 4                       # channel held by K position `pos`
+    chan = torch.tensor([PI[8 * ((p % 16) // 4) + 4 * (p // 16) + (p % 4)] for p in range(32)], device=dev)
     n = torch.arange(co, device=dev)
     src_chunk = torch.arange(4, device=dev)[None, :] ^ ((n >> 1) & 3)[:, None]   # destination chunk c holds source chunk c ^ x
     out = []
     for t in parts:
-        t = t.reshape(k, co, ci // 32, 32)[..., chan]              # permuted K order
+        t = t.reshape(k, co, ci // 32, 32)[..., chan]              # K order of the kernel
         t = t.permute(0, 2, 1, 3).reshape(k, ci // 32, co, 4, 8)   # [k, kb, co, chunk, 8 halves]
         t = torch.gather(t, 3, src_chunk[None, None, :, :, None].expand(k, ci // 32, co, 4, 8))
         out.append(t.reshape(k, ci // 32, co, 32))
     return torch.stack(out, 2).contiguous()                        # [k, kb, nsplit, co, 32]
 
 
+def pack_weight_grp(w, nsplit=1):
+    """w [n_off, C_out, C_in] (logical channels) -> the B-operand image of the group kernel (csrc/tl_conv_grp.cu):
+    [n_off, C_in/32, nsplit, C_out, 32] fp16; K position m of a 32-channel block = logical channel PI[m] (the memory order of
+    a P-layout row, which cp.async copies verbatim), rows carry the SWIZZLE_64B image; nsplit = 2: (hi, lo) slab pairs."""
+    k, co, ci = w.shape
+    assert ci % 32 == 0 and co % 32 == 0, (ci, co)
+    w = w.detach().float()
+    hi = w.half()
+    parts = [hi] if nsplit == 1 else [hi, (w - hi.float()).half()]
+    dev = w.device
+    chan = torch.tensor(PI, device=dev)
+    n = torch.arange(co, device=dev)
+    src_chunk = torch.arange(4, device=dev)[None, :] ^ ((n >> 1) & 3)[:, None]
+    out = []
+    for t in parts:
+        t = t.reshape(k, co, ci // 32, 32)[..., chan]
+        t = t.permute(0, 2, 1, 3).reshape(k, ci // 32, co, 4, 8)
+        t = torch.gather(t, 3, src_chunk[None, None, :, :, None].expand(k, ci // 32, co, 4, 8))
+        out.append(t.reshape(k, ci // 32, co, 32))
+    return torch.stack(out, 2).contiguous()
+
+
+def pack_weight(w, nsplit=1):
+    """Weights for the active f16 / f16x2 kernel (TL_TS)."""
+    return pack_weight_grp(w, nsplit) if TS_KIND == 1 else pack_weight_ts(w, nsplit)
+
+
+def permute_p_weight(w):
+    """w [n_off, C_out, C_in] logical -> both channel axes in P-layout order, for kernels with natural addressing (fp32 SIMT,
+    round 1's TF32 kernel) that read and write P-layout tensors (the 1x1 projection of the fp32 residual stream)."""
+    k, co, ci = w.shape
+    pi = torch.tensor(PI, device=w.device)
+    w = w.reshape(k, co // 32, 32, ci // 32, 32)[:, :, pi][:, :, :, :, pi]
+    return w.reshape(k, co, ci).contiguous()
+
+
 def to_split(x):
-    """fp32 [rows, C] -> the f16x2 operand format [rows, C/32, 2, 32] fp16 (returned as [rows, 2C])."""
+    """fp32 [rows, C] logical -> the f16x2 operand format: P-layout, per 32-channel block 64 B of hi halves then 64 B of lo
+    halves ([rows, C/32, 2, 32] fp16, returned as [rows, 2C])."""
+    x = to_p(x)
     r, c = x.shape
     hi = x.half()
     lo = (x - hi.float()).half()
@@ -254,7 +311,7 @@ def to_split(x):
 def from_split(x):
     r, c2 = x.shape
     v = x.reshape(r, c2 // 64, 2, 32).float()
-    return (v[:, :, 0] + v[:, :, 1]).reshape(r, c2 // 2)
+    return from_p((v[:, :, 0] + v[:, :, 1]).reshape(r, c2 // 2))
 
 
 SPLITK_MAX_ROWS = 2 * 148 * TILE_ROWS   # below two waves of 128-row tiles the library may split K over CTAs
@@ -329,7 +386,7 @@ def heads(voxel_feats, v2p, packed, split=False):
     feats = torch.empty((n, c), dtype=torch.float32, device=dev)
     logits = torch.empty((n, 2), dtype=torch.float32, device=dev)
     offs = torch.empty((n, 3), dtype=torch.float32, device=dev)
-    fmt = 0 if voxel_feats.dtype == torch.float32 else (2 if split else 1)
+    fmt = 0 if voxel_feats.dtype == torch.float32 else (2 if split else (3 if USE_TS else 1))
     check(lib.tl_heads_fwd(ptr(voxel_feats), fmt, ptr(v2p), n, c, ptr(packed['sem_w1']), ptr(packed['sem_b1']),
                            ptr(packed['sem_w2']), ptr(packed['sem_b2']), ptr(packed['off_w1']), ptr(packed['off_b1']),
                            ptr(packed['off_w2']), ptr(packed['off_b2']), ptr(feats), ptr(logits), ptr(offs),
