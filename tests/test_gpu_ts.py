@@ -56,7 +56,7 @@ def test_ts_subm_conv_parity(nsplit, ci, co):
         assert torch.allclose(sparse.from_p(act2.float()).cpu().double(), a2, atol=3e-3, rtol=2e-3)
     else:
         assert torch.allclose(sparse.from_split(act).cpu().double(), a1, **X2_TOL)
-        assert torch.allclose(sparse.from_split(act2).cpu().double(), a2, atol=1e-4, rtol=2e-5)   # scale up to ~4 amplifies the raw error
+        assert torch.allclose(sparse.from_split(act2).cpu().double(), a2, atol=4e-4, rtol=6e-5)   # scale up to ~5 amplifies the raw error
 
 
 @pytest.mark.parametrize('nsplit', [1, 2])

@@ -1,6 +1,7 @@
-"""Timeline of k_conv_ts on SM 0 (TRACE build, TL_TS_DEBUG bit 32) for one submanifold conv of the cfg2 tile.
+"""Timeline of the f16 conv kernel on SM 0 (TRACE build, TL_GRP_DEBUG / TL_TS_DEBUG bit 32) for one submanifold conv of the cfg2 tile.
     make -C treelearn_b200/csrc TRACE=1
-    TL_LIB=treelearn_b200/libtreelearn_b200_trace.so TL_TS_DEBUG=32 python tools/trace_ts.py [32|64|96|128] [f16|f16x2]
+    TL_LIB=treelearn_b200/libtreelearn_b200_trace.so TL_GRP_DEBUG=32 python tools/trace_ts.py [32|64|96|128] [f16|f16x2]
+    (TL_TS=2 TL_TS_DEBUG=32 ... for the tensor-memory-A kernel)
 Events (tag = tile ordinal << 3 | event) of the four warps of group 0 on CTA 0 (roles 0..3):
   0 tile begins, 1 main loop done, 2 accumulator complete, 3 epilogue done"""
 import ctypes as C
@@ -13,7 +14,8 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from treelearn_b200 import _lib, sparse, synth  # noqa: E402
 
-assert int(os.environ.get('TL_TS_DEBUG', '0')) & 32, 'run with TL_TS_DEBUG=32 and the TRACE build (TL_LIB=...)'
+KIND = 'grp' if os.environ.get('TL_TS', '1') == '1' else 'ts'     # which kernel mode f16 dispatches to (csrc/tl_conv_simt.cu)
+assert int(os.environ.get(f'TL_{KIND.upper()}_DEBUG', '0')) & 32, f'run with TL_{KIND.upper()}_DEBUG=32 and the TRACE build (TL_LIB=...)'
 c_ch = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 mode = sys.argv[2] if len(sys.argv) > 2 else 'f16'
 nsplit = 2 if mode == 'f16x2' else 1
@@ -25,7 +27,7 @@ lv = sparse.build_levels(keys, vc, [1000, 1000, 1000], level + 1)[level]
 g = torch.Generator(device='cuda').manual_seed(0)
 x = torch.randn((lv.n, c_ch), device='cuda', generator=g)
 x = sparse.to_split(x) if nsplit == 2 else x.half()
-w = sparse.pack_weight_ts(torch.randn((27, c_ch, c_ch), device='cuda', generator=g) / 30, nsplit)
+w = sparse.pack_weight(torch.randn((27, c_ch, c_ch), device='cuda', generator=g) / 30, nsplit)
 s, t = torch.ones(c_ch, device='cuda'), torch.zeros(c_ch, device='cuda')
 m = _lib.MODE_F16X2 if nsplit == 2 else _lib.MODE_F16
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -39,7 +41,7 @@ print(f'level {level}: {lv.n} voxels, {tiles} tiles ({tiles / 148:.1f} per SM), 
 lib = C.CDLL(_lib.LIB_PATH)
 ROLES, LEN = 8, 4096
 buf = np.zeros(ROLES * LEN, dtype=np.uint64)
-assert lib.tl_debug_copy_trace_ts(C.c_void_p(buf.ctypes.data), C.c_size_t(buf.nbytes)) == 0
+assert getattr(lib, f'tl_debug_copy_trace_{KIND}')(C.c_void_p(buf.ctypes.data), C.c_size_t(buf.nbytes)) == 0
 buf = buf.reshape(ROLES, LEN)
 tag, clk = (buf >> np.uint64(48)).astype(np.int64), (buf & np.uint64((1 << 48) - 1)).astype(np.int64)
 ev = {}

@@ -11,12 +11,15 @@
 // cross-role hand-off on the critical path.  The CTA (one per SM, persistent) is split into G independent GROUPS of four
 // warps.  A group owns one 128-row tile at a time, a private accumulator in tensor memory and a private ring of R A
 // stages in shared memory, and does everything for its tile:
-//   * gather: thread (piece c = t & 3, sub-row t >> 2) copies the 16 B piece c of rows sub, sub + 32, sub + 64, sub + 96 of
-//     the chunk (a chunk = 128 neighbour rows x 32 channels of one (segment, offset, k-block)) with cp.async.cg into the
-//     SWIZZLE_64B K-major stage; absent neighbours read one of 256 spread-out zero rows (uniform 16 B copies);
-//     completion = cp.async.mbarrier.arrive.noinc on the stage's `full` barrier -- nobody waits for its own copies;
-//   * the group's first warp, D chunks behind its own gather front, waits for `full` of the oldest chunk (normally
-//     complete) and its elected lane issues the tcgen05.mma K steps + tcgen05.commit -> the stage's `empty` barrier;
+//   * gather (warps 1-3 of the group, chunk i of the tile by warp 1 + i % 3): ONE warp copies all 128 neighbour rows of a
+//     chunk (a chunk = 128 rows x 32 channels of one (segment, offset, k-block)) -- lane (piece c = lane & 3, sub-row lane >> 2)
+//     the 16 B piece c of rows sub + 8 i, i = 0..15 -- with cp.async.cg into the SWIZZLE_64B K-major stage, so the per-chunk
+//     bookkeeping is paid once per 16 copies (with 4 copies per thread the kernel was instruction-bound, profiles/
+//     r02_conv_history.md); the rulebook entries come straight from global memory one chunk ahead; absent neighbours read one
+//     of 256 spread-out zero rows (uniform 16 B copies); completion = cp.async.mbarrier.arrive.noinc on the stage's `full`
+//     barrier -- nobody waits for its own copies;
+//   * the group's first warp waits for `full` of the chunks in order and its elected lane issues the tcgen05.mma K steps +
+//     tcgen05.commit -> the stage's `empty` barrier;
 //   * epilogue: the group's four warps are the four TMEM lane quarters; tcgen05.ld.16x256b hands every lane 8 channels of
 //     4 rows, written as 16 B / 32 B vectors that a quad of lanes makes a contiguous row piece: no shared memory.
 // Weights: resident in shared memory when the layer fits (C = 32: 54 KB), else one stream per CTA (TMA bulk copies into
@@ -43,7 +46,7 @@ constexpr int MAX_NB = 64;                 // weight ring slots
 constexpr int MAX_LIST = 448;              // live chunks of a tile
 constexpr int LIST_BYTES = MAX_LIST * 4 + 16;
 constexpr int GROUP_SMEM = LIST_BYTES;     // per group, beside its A ring: the tile's chunk list
-constexpr int IDXQ = 4;                    // rulebook entries are fetched (LDG) this many chunks ahead of their gather
+constexpr int GW = 3;                      // gather warps per group; chunk i of a tile is gathered by warp 1 + i % GW
 constexpr int TMEM_COLS = 512;
 
 // 256 zero regions of 1 KB: source of absent neighbour rows (never written).  Spread out so the reads do not serialise on
@@ -145,7 +148,7 @@ __global__ void __launch_bounds__(32 * (4 * G + (RESIDENT ? 0 : 1)), 1) k_conv_g
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int N = d.c_out;
-    const uint32_t R = (uint32_t)P.R, NB = (uint32_t)P.nb, D = (uint32_t)P.D;
+    const uint32_t R = (uint32_t)P.R, NB = (uint32_t)P.nb;
     const Layout L = carve(base, P.b_bytes, G, P.R, STAGE);
     const uint32_t slab = (uint32_t)N * 64u * NSPLIT;   // weight bytes of one chunk: [C_out][32] fp16 (x hi, lo)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -155,7 +158,7 @@ __global__ void __launch_bounds__(32 * (4 * G + (RESIDENT ? 0 : 1)), 1) k_conv_g
     if (threadIdx.x == 0) {
         for (int g = 0; g < G; ++g) {
             for (uint32_t r = 0; r < R; ++r) {
-                mbar_init(L.full(g, r), 128);           // every thread of the group: its copies of the chunk have landed
+                mbar_init(L.full(g, r), 32);            // the lanes of the warp that gathered the chunk: their copies have landed
                 mbar_init(L.empty(g, r), 1);            // tcgen05.commit of the MMAs that read the stage
             }
             mbar_init(L.acc_full(g), 1);
@@ -225,14 +228,14 @@ __global__ void __launch_bounds__(32 * (4 * G + (RESIDENT ? 0 : 1)), 1) k_conv_g
         // ===================== a group: gather -> MMA -> epilogue for its own tiles =================
         const int g = warp >> 2, qtr = warp & 3;
         const int q = lane & 3, rr = lane >> 2;          // epilogue: piece q of rows rr + 8 i of my lane quarter
-        const int tig = threadIdx.x & 127;                // thread in group
-        const int pc = tig & 3, sub = tig >> 2;           // gather: 16 B piece pc of rows sub + 32 j
+        const int pc = lane & 3, sub = lane >> 2;         // gather: 16 B piece pc of rows sub + 8 i, i = 0..15
+        const int gw = qtr - 1;                           // gather warps 0..2 of the group (warp 0 issues the MMAs)
         const int bar_id = 1 + g;
         const uint32_t lane_field = ((uint32_t)qtr * 32u) << 16;
         const uint32_t acc_col = tmem_base + (uint32_t)(g * P.acc_cols);
         const uint32_t ring = L.a0 + (uint32_t)g * L.a_group_bytes;
         const uint32_t listbuf = L.grp0 + (uint32_t)g * GROUP_SMEM;
-        // 16 B piece c of row r lives at c ^ ((r >> 1) & 3) (SWIZZLE_64B); rows sub + 32 j share the swizzle term
+        // 16 B piece c of row r lives at c ^ ((r >> 1) & 3) (SWIZZLE_64B); rows sub + 8 i share the swizzle term
         const uint32_t dst_thr = (uint32_t)(sub * 64 + ((pc ^ ((sub >> 1) & 3)) << 4));
         const bool leader = qtr == 0;
         const uint32_t idesc = make_idesc(N, true);
@@ -241,7 +244,8 @@ __global__ void __launch_bounds__(32 * (4 * G + (RESIDENT ? 0 : 1)), 1) k_conv_g
         const uint32_t slab16 = slab >> 4, half16 = ((uint32_t)N * 64u) >> 4, stage16 = STAGE >> 4, ahalf16 = ((uint32_t)BM * 64u) >> 4;
         const uint64_t zero_src = (uint64_t)g_zero_rows_grp + (uint32_t)(pc * 16);
         const bool trg = kTrace && (dbg & 32) && blockIdx.x == 0 && g == 0 && lane == 0;
-        uint32_t tp = 0;
+        const bool trc = trg && qtr == 1, trl = trg && qtr == 0;      // per-chunk events of gather warp 1 / the MMA warp
+        uint32_t tp = 0, tp2 = 0;
         // per-segment source: base + this thread's piece, bytes per row (TL_MAX_SEG == 3)
         uint64_t src0 = 0, src1 = 0, src2 = 0;
         uint32_t rb0 = 0, rb1 = 0, rb2 = 0;
@@ -286,7 +290,7 @@ __global__ void __launch_bounds__(32 * (4 * G + (RESIDENT ? 0 : 1)), 1) k_conv_g
         };
 
         if (RESIDENT) mbar_wait(L.wres(), 0u);
-        uint32_t g_slot = 0, g_phase = 0;       // gather front in this group's A ring
+        uint32_t g_slot = 0, g_phase = 0;       // ring position of the tile's first chunk
         uint32_t m_slot = 0, m_phase = 0;       // MMA front (first warp)
         uint32_t b_slot = 0, b_phase = 0;       // position in the CTA's weight stream (streaming mode; first warp)
         if (leader) build_list((int)blockIdx.x * G + g);
@@ -296,45 +300,47 @@ __global__ void __launch_bounds__(32 * (4 * G + (RESIDENT ? 0 : 1)), 1) k_conv_g
             const int tile = (r * (int)gridDim.x + (int)blockIdx.x) * G + g;
             const bool valid = tile < P.num_tiles;
             const uint32_t n = ld_shared_u32(listbuf + 4u * MAX_LIST);
-            const uint32_t zr0 = (uint32_t)tile * 37u + (uint32_t)sub * 16u;
+            const uint32_t zr0 = (uint32_t)tile * 37u + (uint32_t)sub * 32u;
             trace(trg, qtr, tp, ((uint32_t)r << 3) | 0u);
 
-            // ---- rulebook entries of chunk i (rows sub + 32 j of the tile) -> registers, IDXQ chunks ahead of its gather
-            auto load_idx = [&](uint32_t i, int (&ix)[4]) {
+            // ---- rulebook entries of chunk i (rows sub + 8 j of the tile, j = 0..15) -> registers, one chunk ahead of its gather
+            auto load_idx = [&](uint32_t i, int (&ix)[16]) {
                 const uint32_t e = ld_shared_u32(listbuf + 4u * i);
                 const int s = (int)(e & 3u);
                 const int32_t* ip = sel3(s, ip0, ip1, ip2);
                 if (ip) {
                     ip += (size_t)((e >> 5) & 31u) * sel3(s, is0, is1, is2) + (size_t)tile * BM;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) ix[j] = __ldg(ip + 32 * j);
+                    for (int j = 0; j < 16; ++j) ix[j] = __ldg(ip + 8 * j);
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) ix[j] = (tile * BM + sub + 32 * j < d.n_out) ? tile * BM + sub + 32 * j : -1;
+                    for (int j = 0; j < 16; ++j) ix[j] = (tile * BM + sub + 8 * j < d.n_out) ? tile * BM + sub + 8 * j : -1;
                 }
             };
-            // ---- gather chunk i of the list into the stage at the gather front
-            auto gather = [&](uint32_t i, const int (&ix)[4]) {
+            // ---- one warp gathers all 128 rows of chunk i into stage (slot, phase)
+            auto gather = [&](uint32_t i, const int (&ix)[16], uint32_t slot, uint32_t phase) {
                 const uint32_t e = ld_shared_u32(listbuf + 4u * i);
                 const int s = (int)(e & 3u);
                 const uint32_t kboff = ((e >> 2) & 7u) * (64u * NSPLIT);
                 const uint64_t src = sel3(s, src0, src1, src2) + kboff;
                 const uint32_t rb = sel3(s, rb0, rb1, rb2);
-                mbar_wait(L.empty(g, g_slot), g_phase ^ 1u);
-                const uint32_t dst = ring + g_slot * STAGE + dst_thr;
+                trace(trc, 5, tp2, (i << 3) | 0u);
+                mbar_wait(L.empty(g, slot), phase ^ 1u);
+                trace(trc, 5, tp2, (i << 3) | 1u);
+                const uint32_t dst = ring + slot * STAGE + dst_thr;
                 if (!(dbg & 2)) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
+                    for (int j = 0; j < 16; ++j) {
                         // absent neighbours read one of 256 spread-out zero rows: every copy is a uniform 16 B
                         const uint64_t z = zero_src + (((zr0 + (uint32_t)j) & 255u) << 10);
                         const uint64_t p = ix[j] >= 0 ? src + (uint64_t)(uint32_t)ix[j] * rb : z;
-                        cp_async16_cg(dst + (uint32_t)(j * 32 * 64), reinterpret_cast<const void*>(p), 16u);
+                        cp_async16_cg(dst + (uint32_t)(j * 8 * 64), reinterpret_cast<const void*>(p), 16u);
                         if (NSPLIT == 2)
-                            cp_async16_cg(dst + (uint32_t)(BM * 64 + j * 32 * 64), reinterpret_cast<const void*>(ix[j] >= 0 ? p + 64 : z), 16u);
+                            cp_async16_cg(dst + (uint32_t)(BM * 64 + j * 8 * 64), reinterpret_cast<const void*>(ix[j] >= 0 ? p + 64 : z), 16u);
                     }
                 }
-                cp_async_mbar_arrive_noinc(L.full(g, g_slot));
-                if (++g_slot == R) g_slot = 0, g_phase ^= 1u;
+                cp_async_mbar_arrive_noinc(L.full(g, slot));
+                trace(trc, 5, tp2, (i << 3) | 2u);
             };
             // ---- first warp: issue the MMAs of chunk i (its stage = the MMA front)
             uint32_t b_next = 0;                // next unconsumed ordinal of this round (streaming mode)
@@ -356,7 +362,9 @@ __global__ void __launch_bounds__(32 * (4 * G + (RESIDENT ? 0 : 1)), 1) k_conv_g
                     mbar_wait(L.b_full(b_slot), b_phase);
                     boff = b_slot * slab16;
                 }
+                trace(trl, 4, tp2, (i << 3) | 0u);
                 mbar_wait(L.full(g, m_slot), m_phase);
+                trace(trl, 4, tp2, (i << 3) | 1u);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // cp.async (generic proxy) writes -> tensor core reads
                 tc_fence_after();
                 if (elect_one()) {
@@ -376,6 +384,7 @@ __global__ void __launch_bounds__(32 * (4 * G + (RESIDENT ? 0 : 1)), 1) k_conv_g
                     if (!RESIDENT) umma_commit(L.b_empty(b_slot));
                 }
                 __syncwarp();
+                trace(trl, 4, tp2, (i << 3) | 2u);
                 if (!RESIDENT) {
                     ++b_next;
                     if (++b_slot == NB) b_slot = 0, b_phase ^= 1u;
@@ -383,22 +392,37 @@ __global__ void __launch_bounds__(32 * (4 * G + (RESIDENT ? 0 : 1)), 1) k_conv_g
                 if (++m_slot == R) m_slot = 0, m_phase ^= 1u;
             };
 
-            int ixq[IDXQ][4];
-#pragma unroll
-            for (int u = 0; u < IDXQ; ++u)
-                if ((uint32_t)u < n) load_idx((uint32_t)u, ixq[u]);
-            for (uint32_t i0 = 0; i0 < n; i0 += IDXQ) {
-#pragma unroll
-                for (int u = 0; u < IDXQ; ++u) {
-                    const uint32_t i = i0 + (uint32_t)u;
+            if (!leader) {
+                // gather warp gw takes chunks gw, gw + GW, ...; the ring position of chunk i is (ring_pos + i) mod R
+                uint32_t slot = g_slot + (uint32_t)gw, phase = g_phase;
+                while (slot >= R) slot -= R, phase ^= 1u;
+                int ixa[16], ixb[16];
+                uint32_t i = (uint32_t)gw;
+                if (i < n) load_idx(i, ixa);
+                while (i < n) {
+                    if (i + GW < n) load_idx(i + GW, ixb);
+                    gather(i, ixa, slot, phase);
+                    slot += GW;
+                    while (slot >= R) slot -= R, phase ^= 1u;
+                    i += GW;
                     if (i >= n) break;
-                    gather(i, ixq[u]);
-                    if (i + IDXQ < n) load_idx(i + IDXQ, ixq[u]);
-                    if (leader && i >= D) issue(i - D);
+                    if (i + GW < n) load_idx(i + GW, ixa);
+                    gather(i, ixb, slot, phase);
+                    slot += GW;
+                    while (slot >= R) slot -= R, phase ^= 1u;
+                    i += GW;
                 }
+            } else {
+                // the first warp issues the MMAs in chunk order as the stages fill
+                for (uint32_t i = 0; i < n; ++i) issue(i);
+            }
+            // ring position of the next tile's first chunk
+            for (uint32_t left = n; left;) {     // (no integer division: n is a few dozen)
+                const uint32_t step = min(left, R - g_slot);
+                g_slot += step, left -= step;
+                if (g_slot == R) g_slot = 0, g_phase ^= 1u;
             }
             if (leader) {
-                for (uint32_t i = n > D ? n - D : 0u; i < n; ++i) issue(i);
                 if (!RESIDENT) skip_to((uint32_t)P.chunks_total);      // release the rest of this round's weight stream
                 if (elect_one()) {
                     if (n) umma_commit(L.acc_full(g));
@@ -587,12 +611,12 @@ int conv_fwd_grp(const tl_conv_desc& d, cudaStream_t stream, int nsplit) {
             if (G * n > grp::TMEM_COLS) continue;
             for (int R = grp::MAX_R; R >= 3; --R) {
                 if (grp::smem_bytes(bmin, G, R, stage) > budget) continue;
-                const int score = G * (R - 2);
+                const int score = G * (R - 1 < 4 ? R - 1 : 4);   // stages beyond 5 per group add nothing: 3 gather warps + MMA
                 if (score > best_score) best_score = score, bestG = G, bestR = R, best_res = res;
                 break;
             }
         }
-        if (best_score >= 6) break;     // resident weights with enough gather depth: take it
+        if (best_score >= 9) break;     // resident weights with enough gather depth: take it
     }
     if (env_int_grp("TL_GRP_GROUPS", 0) > 0) {      // experiments: force G, largest R that fits
         bestG = env_int_grp("TL_GRP_GROUPS", 0);
@@ -607,9 +631,7 @@ int conv_fwd_grp(const tl_conv_desc& d, cudaStream_t stream, int nsplit) {
     }
     const int G = bestG;
     P.R = bestR;
-    P.D = env_int_grp("TL_GRP_D", bestR > 3 ? bestR - 2 : bestR - 1);
-    if (P.D < 1) P.D = 1;
-    if (P.D >= P.R) P.D = P.R - 1;
+    P.D = 0;
     P.acc_cols = n;
     P.resident = best_res;
     if (P.resident) {

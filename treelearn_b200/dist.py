@@ -42,29 +42,63 @@ def allgather_rows(t, group=None):
     return torch.cat([o[:s] for o, s in zip(out, sizes)], dim=0)
 
 
-def segment_plot(model, tiles, grouping_cfg, group=None):
+def allgather_rows_known(t, sizes, group=None):
+    """Variable-length all-gather along dim 0 when every rank already knows all row counts `sizes` (one per rank):
+    ONE collective (`all_gather_into_tensor`) on a buffer sized for the largest contribution, no size exchange."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return t
+    world = dist.get_world_size(group)
+    assert len(sizes) == world and t.shape[0] == sizes[dist.get_rank(group)]
+    m = max(max(sizes), 1)
+    pad = torch.zeros((m,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    pad[:t.shape[0]] = t
+    out = torch.empty((world * m,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out, pad, group=group)
+    return torch.cat([out[r * m:r * m + s] for r, s in enumerate(sizes)], dim=0)
+
+
+def segment_plot(model, tiles, grouping_cfg, group=None, marks=None):
     """Whole-plot inference (BASELINE.json config 4): `tiles` is the same list of host batch dicts on every rank.
-    Returns (merged coords [P,3], instance labels [P]) as CUDA tensors, identical on every rank."""
+    Returns (merged coords [P,3], instance labels [P], n_clusters) as CUDA tensors, identical on every rank.
+    `marks` (optional list) receives (name, cuda event) pairs at the stage boundaries: forward, allgather, merge, cluster."""
     from . import pipeline
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1
-    mine = shard_indices([t['coords'].shape[0] for t in tiles], rank, world)
+    owner = [None] * len(tiles)
+    for r in range(world):
+        for i in shard_indices([t['coords'].shape[0] for t in tiles], r, world):
+            owner[i] = r
+    mine = [i for i, r in enumerate(owner) if r == rank]
+    # every rank holds every tile's inner mask, so all row counts are known without a size exchange
+    sizes = [sum(int(tiles[i]['masks_inner'].sum()) for i in range(len(tiles)) if owner[i] == r) for r in range(world)]
+
+    def mark(name):
+        if marks is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            marks.append((name, e))
+
     rows = []
     dev = torch.device('cuda', torch.cuda.current_device())
+    mark('start')
     with torch.no_grad():
         model.eval()
         for i in mine:
             b = tiles[i]
             out = model(b, return_loss=False)
-            inner = b['masks_inner'].to(dev)
-            xyz = (b['coords'] + b['centers']).to(dev)[inner]
+            inner = b['masks_inner'].to(dev, non_blocking=True)
+            xyz = (b['coords'] + b['centers']).to(dev, non_blocking=True)[inner]
             rows.append(torch.cat([xyz, out['semantic_prediction_logits'][inner], out['offset_predictions'][inner],
-                                   b['input_feats'].to(dev)[inner][:, -1:]], dim=1))
+                                   b['input_feats'].to(dev, non_blocking=True)[inner][:, -1:]], dim=1))
     local = torch.cat(rows) if rows else torch.zeros((0, 9), device=dev)
-    allrows = allgather_rows(local.contiguous(), group)          # the one collective of the inference path
+    mark('forward')
+    allrows = allgather_rows_known(local.contiguous(), sizes, group)          # the one collective of the inference path
+    mark('allgather')
     coords, vals = pipeline.ensemble_cuda(allrows[:, :3].contiguous(), allrows[:, 3:].contiguous())
+    mark('merge')
     labels, n_clusters = pipeline.instances_cuda(coords, vals[:, 2:5].contiguous(), vals[:, 0:2].contiguous(),
                                                  vals[:, 5].contiguous(), grouping_cfg)
+    mark('cluster')
     return coords, labels, n_clusters
 
 

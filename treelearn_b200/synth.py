@@ -94,6 +94,34 @@ def make_batch(tiles, inner_edge=8.0):
             'offset_labels': torch.cat(off), 'batch_size': len(tiles), 'centers': torch.cat(cen).float()}
 
 
+def plot_tiles(n_side=8, inner_edge=8.0, outer_edge=13.5, stride=0.5, seed=7, trees_per_100m2=5.6, ground_density=1000.0):
+    """BASELINE.json config 4: ONE synthetic plot cut into n_side x n_side overlapping tiles (inner squares of `inner_edge`
+    stepped by stride * inner_edge, `outer_edge` of context on every side => 35 m tiles at the defaults, every interior
+    point in (1 / stride)^2 = 4 inner squares), as `SampleGenerator.tile_generate_and_save` lays them out
+    (tree_learn/util/data_preparation.py:364-431).  Returns the list of model input dicts (TreeDataset test-mode fields the
+    inference path reads: coords centred on the tile, input_feats, batch_ids, batch_size, masks_inner, centers)."""
+    step = stride * inner_edge
+    span = (n_side - 1) * step + inner_edge                    # union of the inner squares
+    edge = span + 2 * outer_edge
+    f = synth_forest(edge=edge, n_trees=int(round(trees_per_100m2 * edge * edge / 100.0)), seed=seed, ground_density=ground_density)
+    xyz, feat = f['coords'], f['feat']                         # plot coordinates, xy-centred
+    first = -span / 2 + inner_edge / 2
+    tiles = []
+    for iy in range(n_side):
+        for ix in range(n_side):
+            cx, cy = np.float32(first + ix * step), np.float32(first + iy * step)
+            half = np.float32(inner_edge / 2 + outer_edge)
+            sel = (np.abs(xyz[:, 0] - cx) <= half) & (np.abs(xyz[:, 1] - cy) <= half)
+            p = xyz[sel] - np.array([cx, cy, 0], dtype=np.float32)
+            n = len(p)
+            inner = (np.abs(p[:, 0]) <= inner_edge / 2) & (np.abs(p[:, 1]) <= inner_edge / 2)
+            tiles.append({'coords': torch.from_numpy(p), 'input_feats': torch.from_numpy(feat[sel]).reshape(-1, 1),
+                          'batch_ids': torch.zeros(n, dtype=torch.long), 'batch_size': 1,
+                          'masks_inner': torch.from_numpy(inner),
+                          'centers': torch.from_numpy(np.array([cx, cy, 0], dtype=np.float32)).reshape(1, 3).expand(n, 3).contiguous()})
+    return tiles
+
+
 # named workloads (BASELINE.json configs; sizes per SURVEY §8d)
 WORKLOADS = {
     'cfg1_200k': dict(edge=20.0, n_trees=20, seed=0),
@@ -119,3 +147,37 @@ def randomize_bn_stats(model, seed=0):
                 m.running_mean.copy_(0.1 * torch.randn(c, generator=g))
                 m.running_var.copy_(0.5 + torch.rand(c, generator=g))
     return model
+
+
+def fit_probe_heads(model, batch, ridge=1e-3):
+    """"Trained-like" heads for a random-init backbone (there is no network for the reference's checkpoint): the last
+    Linear of both heads is fitted by ridge regression on THIS model's own hidden activations so that
+      * offset_predictions approximate the tile's offset labels on tree points (vectors of several metres, like a trained
+        model's: tree_learn/dataset/dataset.py:111-140), and
+      * the semantic logits separate tree / non-tree points.
+    Everything before the last Linear stays as initialised, so the backbone arithmetic that parity tests probe is untouched.
+    `model` must be on the GPU in eval mode; the fitted weights are written into `model` and also returned as a dict of
+    CPU tensors keyed like the state_dict ('offset_linear.3.weight', ...)."""
+    dev = next(model.parameters()).device
+    with torch.no_grad():
+        out = model(batch, return_loss=False)
+        feats = out['backbone_feats'].double()
+        fitted = {}
+        tree = (batch['semantic_labels'] == TREE_CLASS).to(dev)
+        for name, head, target, rows in (
+                ('offset_linear', model.offset_linear, batch['offset_labels'].to(dev).double(), tree),
+                ('semantic_linear', model.semantic_linear,
+                 torch.where(tree, 4.0, -4.0)[:, None].double() * torch.tensor([1.0, -1.0], device=dev, dtype=torch.float64),
+                 torch.ones_like(tree))):
+            bn = head[1]
+            h = head[0].weight.double() @ feats.T + head[0].bias.double()[:, None]
+            h = (h - bn.running_mean.double()[:, None]) / torch.sqrt(bn.running_var.double()[:, None] + bn.eps)
+            h = torch.relu(h * bn.weight.double()[:, None] + bn.bias.double()[:, None]).T            # [N, C]
+            a = torch.cat([h[rows], torch.ones((int(rows.sum()), 1), device=dev, dtype=torch.float64)], 1)
+            gram = a.T @ a + ridge * len(a) * torch.eye(a.shape[1], device=dev, dtype=torch.float64)
+            sol = torch.linalg.solve(gram, a.T @ target[rows])                                       # [C + 1, out]
+            w, b = sol[:-1].T.float().contiguous(), sol[-1].float().contiguous()
+            head[3].weight.copy_(w)
+            head[3].bias.copy_(b)
+            fitted[name + '.3.weight'], fitted[name + '.3.bias'] = w.cpu(), b.cpu()
+    return fitted
