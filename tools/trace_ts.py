@@ -70,3 +70,51 @@ for w in range(4):
     stat(f'warp {w}: epilogue done -> next tile begins', [ev[(w, r + 1, 0)] - ev[(w, r, 3)] for r in R_ if (w, r + 1, 0) in ev])
 if len(R_) > 2:
     print(f'group 0: {(ev[(0, R_[-1], 3)] - ev[(0, R_[0], 3)]) / (len(R_) - 1):.0f} cycles per tile in steady state')
+
+# ---- per-chunk events (group kernel): role 4 = the group's MMA warp (0 begin wait full, 1 full seen, 2 MMAs + commit issued),
+#      role 5 = gather warp 1 (0 begin wait for a free stage, 1 stage free, 2 copies issued + arrive)
+def seq(role):
+    out = []
+    for p in range(LEN):
+        if buf[role, p] == 0:
+            break
+        out.append((int(tag[role, p]) & 7, int(tag[role, p]) >> 3, int(clk[role, p])))
+    return out
+
+
+def deltas(events, a, b):
+    return [events[k + 1][2] - events[k][2] for k in range(len(events) - 1) if events[k][0] == a and events[k + 1][0] == b]
+
+
+m, gth = seq(4), seq(5)
+if m:
+    m = m[60:]
+    stat('MMA warp per chunk: wait for full', deltas(m, 0, 1))
+    stat('MMA warp per chunk: fence + MMAs + commit', deltas(m, 1, 2))
+    stat('MMA warp per chunk: commit -> next wait (same tile)', [d for d, e in zip(deltas(m, 2, 0), [x for x in m if x[0] == 2]) if True])
+    per = [m[k + 3][2] - m[k][2] for k in range(0, len(m) - 3) if m[k][0] == 0 and m[k + 3][0] == 0 and m[k + 3][1] == m[k][1] + 1]
+    stat('MMA warp: chunk to chunk (same tile)', per)
+if gth:
+    gth = gth[30:]
+    stat('gather warp 1 per own chunk: wait for a free stage', deltas(gth, 0, 1))
+    stat('gather warp 1 per own chunk: address + 16 copies + arrive', deltas(gth, 1, 2))
+    stat('gather warp 1: arrive -> next own chunk begins (incl. index loads)', deltas(gth, 2, 0))
+    # stage latency: copies issued by the gather warp -> the MMA warp sees the chunk full
+    mm = {}
+    tile_no = 0
+    for ev, i, c in seq(4):
+        if ev == 0 and i == 0:
+            tile_no += 1
+        mm[(tile_no, i, ev)] = c
+    tile_no, lat, lat2 = 0, [], []
+    prev_i = 1 << 30
+    for ev, i, c in seq(5):
+        if ev == 0 and i < prev_i:
+            tile_no += 1
+        if ev == 0:
+            prev_i = i
+        if ev == 2 and (tile_no, i, 1) in mm:
+            lat.append(mm[(tile_no, i, 1)] - c)
+        if ev == 1 and (tile_no, i, 2) in mm:
+            pass
+    stat('copies issued -> MMA warp sees the chunk full', lat[10:])

@@ -18,8 +18,10 @@
 //     r02_conv_history.md); the rulebook entries come straight from global memory one chunk ahead; absent neighbours read one
 //     of 256 spread-out zero rows (uniform 16 B copies); completion = cp.async.mbarrier.arrive.noinc on the stage's `full`
 //     barrier -- nobody waits for its own copies;
-//   * the group's first warp waits for `full` of the chunks in order and its elected lane issues the tcgen05.mma K steps +
-//     tcgen05.commit -> the stage's `empty` barrier;
+//   * three chunks (one per gather warp) form a FILL with one `full` / `empty` mbarrier pair: the group's first warp waits for
+//     `full` of the fills in order and its elected lane issues the fill's tcgen05.mma K steps + ONE tcgen05.commit -> `empty`
+//     (with a barrier pair per chunk this warp was the bottleneck: ~550 cycles per chunk for 82 cycles of MMA,
+//     profiles/r02_trace_grp_v5_c32_chunks.txt);
 //   * epilogue: the group's four warps are the four TMEM lane quarters; tcgen05.ld.16x256b hands every lane 8 channels of
 //     4 rows, written as 16 B / 32 B vectors that a quad of lanes makes a contiguous row piece: no shared memory.
 // Weights: resident in shared memory when the layer fits (C = 32: 54 KB), else one stream per CTA (TMA bulk copies into
@@ -41,7 +43,7 @@ namespace grp {
 using namespace tl::tc;
 
 constexpr int MAX_G = 4;
-constexpr int MAX_R = 8;                   // A stages per group
+constexpr int MAX_R = 9;                   // A stages per group (a multiple of GW)
 constexpr int MAX_NB = 64;                 // weight ring slots
 constexpr int MAX_LIST = 448;              // live chunks of a tile
 constexpr int LIST_BYTES = MAX_LIST * 4 + 16;
@@ -74,6 +76,7 @@ struct Launch {
     int acc_cols;      // TMEM columns per group
     int resident;      // 1: every weight slab of the layer stays in shared memory; 0: weight ring of `nb` slabs
     int nb;
+    int fill;          // chunks per full/empty barrier pair: 1, or GW (one chunk per gather warp)
     uint32_t b_bytes;  // shared-memory bytes of the weight region
     int debug;         // TRACE build: 1 skip MMAs, 2 skip row copies, 4 skip epilogue memory ops, 8 skip weight copies
 };
@@ -149,6 +152,7 @@ __global__ void __launch_bounds__(32 * (4 * G + (RESIDENT ? 0 : 1)), 1) k_conv_g
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int N = d.c_out;
     const uint32_t R = (uint32_t)P.R, NB = (uint32_t)P.nb;
+    const uint32_t FILL = (uint32_t)P.fill, F = R / FILL;      // chunks per fill (1 or GW), fill slots of a group's ring
     const Layout L = carve(base, P.b_bytes, G, P.R, STAGE);
     const uint32_t slab = (uint32_t)N * 64u * NSPLIT;   // weight bytes of one chunk: [C_out][32] fp16 (x hi, lo)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -157,9 +161,9 @@ __global__ void __launch_bounds__(32 * (4 * G + (RESIDENT ? 0 : 1)), 1) k_conv_g
 
     if (threadIdx.x == 0) {
         for (int g = 0; g < G; ++g) {
-            for (uint32_t r = 0; r < R; ++r) {
-                mbar_init(L.full(g, r), 32);            // the lanes of the warp that gathered the chunk: their copies have landed
-                mbar_init(L.empty(g, r), 1);            // tcgen05.commit of the MMAs that read the stage
+            for (uint32_t f = 0; f < R / (uint32_t)P.fill; ++f) {     // per fill = 1 stage, or GW stages (one per gather warp)
+                mbar_init(L.full(g, f), 32 * P.fill);    // every lane of the fill's gather warps: its copies have landed
+                mbar_init(L.empty(g, f), 1);            // tcgen05.commit of the MMAs that read the fill
             }
             mbar_init(L.acc_full(g), 1);
         }
@@ -290,8 +294,8 @@ __global__ void __launch_bounds__(32 * (4 * G + (RESIDENT ? 0 : 1)), 1) k_conv_g
         };
 
         if (RESIDENT) mbar_wait(L.wres(), 0u);
-        uint32_t g_slot = 0, g_phase = 0;       // ring position of the tile's first chunk
-        uint32_t m_slot = 0, m_phase = 0;       // MMA front (first warp)
+        uint32_t g_slot = 0, g_phase = 0;       // ring position (in fills) of the tile's first fill
+        uint32_t m_slot = 0, m_phase = 0;       // MMA front (first warp), in fills
         uint32_t b_slot = 0, b_phase = 0;       // position in the CTA's weight stream (streaming mode; first warp)
         if (leader) build_list((int)blockIdx.x * G + g);
         bar_sync(bar_id, 128);
@@ -317,17 +321,14 @@ __global__ void __launch_bounds__(32 * (4 * G + (RESIDENT ? 0 : 1)), 1) k_conv_g
                     for (int j = 0; j < 16; ++j) ix[j] = (tile * BM + sub + 8 * j < d.n_out) ? tile * BM + sub + 8 * j : -1;
                 }
             };
-            // ---- one warp gathers all 128 rows of chunk i into stage (slot, phase)
-            auto gather = [&](uint32_t i, const int (&ix)[16], uint32_t slot, uint32_t phase) {
+            // ---- one warp copies all 128 rows of chunk i into A stage `stage` of the group's ring
+            auto gather = [&](uint32_t i, const int (&ix)[16], uint32_t stage) {
                 const uint32_t e = ld_shared_u32(listbuf + 4u * i);
                 const int s = (int)(e & 3u);
                 const uint32_t kboff = ((e >> 2) & 7u) * (64u * NSPLIT);
                 const uint64_t src = sel3(s, src0, src1, src2) + kboff;
                 const uint32_t rb = sel3(s, rb0, rb1, rb2);
-                trace(trc, 5, tp2, (i << 3) | 0u);
-                mbar_wait(L.empty(g, slot), phase ^ 1u);
-                trace(trc, 5, tp2, (i << 3) | 1u);
-                const uint32_t dst = ring + slot * STAGE + dst_thr;
+                const uint32_t dst = ring + stage * STAGE + dst_thr;
                 if (!(dbg & 2)) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
@@ -339,10 +340,8 @@ __global__ void __launch_bounds__(32 * (4 * G + (RESIDENT ? 0 : 1)), 1) k_conv_g
                             cp_async16_cg(dst + (uint32_t)(BM * 64 + j * 8 * 64), reinterpret_cast<const void*>(ix[j] >= 0 ? p + 64 : z), 16u);
                     }
                 }
-                cp_async_mbar_arrive_noinc(L.full(g, slot));
-                trace(trc, 5, tp2, (i << 3) | 2u);
             };
-            // ---- first warp: issue the MMAs of chunk i (its stage = the MMA front)
+            // ---- first warp: the MMAs of fill f (chunks GW f .. GW f + cnt - 1; stage GW * slot + c), one barrier round trip
             uint32_t b_next = 0;                // next unconsumed ordinal of this round (streaming mode)
             auto skip_to = [&](uint32_t ord) {  // first warp, converged
                 for (; b_next < ord; ++b_next) {
@@ -352,75 +351,93 @@ __global__ void __launch_bounds__(32 * (4 * G + (RESIDENT ? 0 : 1)), 1) k_conv_g
                     if (++b_slot == NB) b_slot = 0, b_phase ^= 1u;
                 }
             };
-            auto issue = [&](uint32_t i) {
-                const uint32_t ord = ld_shared_u32(listbuf + 4u * i) >> 10;
-                uint32_t boff;
-                if (RESIDENT) {
-                    boff = ord * slab16;
-                } else {
-                    skip_to(ord);
-                    mbar_wait(L.b_full(b_slot), b_phase);
-                    boff = b_slot * slab16;
-                }
-                trace(trl, 4, tp2, (i << 3) | 0u);
+            auto issue_fill = [&](uint32_t f) {
+                const uint32_t i0 = FILL * f, cnt = min(FILL, n - i0);
+                trace(trl, 4, tp2, (f << 3) | 0u);
                 mbar_wait(L.full(g, m_slot), m_phase);
-                trace(trl, 4, tp2, (i << 3) | 1u);
+                trace(trl, 4, tp2, (f << 3) | 1u);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // cp.async (generic proxy) writes -> tensor core reads
                 tc_fence_after();
-                if (elect_one()) {
-                    if (!(dbg & 1)) {
-                        const uint64_t ad = adesc0 + (uint64_t)(m_slot * stage16);
-                        const uint64_t bd = bdesc0 + (uint64_t)boff;
 #pragma unroll
-                        for (uint32_t kk = 0; kk < 2; ++kk) {
-                            umma_f16(acc_col, ad + 2 * kk, bd + 2 * kk, idesc, (i | kk) ? 1u : 0u);
-                            if (NSPLIT == 2) {
-                                umma_f16(acc_col, ad + 2 * kk, bd + half16 + 2 * kk, idesc, 1u);            // hi x lo
-                                umma_f16(acc_col, ad + ahalf16 + 2 * kk, bd + 2 * kk, idesc, 1u);           // lo x hi
+                for (uint32_t c = 0; c < (uint32_t)GW; ++c) {
+                    if (c >= cnt) break;
+                    // the weight slab is taken only now: holding ring slots across the A wait can deadlock when the
+                    // tile's list skips more ordinals than the ring has slots
+                    const uint32_t ord = ld_shared_u32(listbuf + 4u * (i0 + c)) >> 10;
+                    uint32_t boff;
+                    if (RESIDENT) {
+                        boff = ord * slab16;
+                    } else {
+                        skip_to(ord);
+                        mbar_wait(L.b_full(b_slot), b_phase);
+                        boff = b_slot * slab16;
+                    }
+                    if (elect_one()) {
+                        if (!(dbg & 1)) {
+                            const uint64_t ad = adesc0 + (uint64_t)((m_slot * FILL + c) * stage16);
+                            const uint64_t bd = bdesc0 + (uint64_t)boff;
+#pragma unroll
+                            for (uint32_t kk = 0; kk < 2; ++kk) {
+                                umma_f16(acc_col, ad + 2 * kk, bd + 2 * kk, idesc, (i0 | c | kk) ? 1u : 0u);
+                                if (NSPLIT == 2) {
+                                    umma_f16(acc_col, ad + 2 * kk, bd + half16 + 2 * kk, idesc, 1u);            // hi x lo
+                                    umma_f16(acc_col, ad + ahalf16 + 2 * kk, bd + 2 * kk, idesc, 1u);           // lo x hi
+                                }
                             }
                         }
+                        if (!RESIDENT) umma_commit(L.b_empty(b_slot));
+                        if (c + 1 == cnt) umma_commit(L.empty(g, m_slot));
                     }
-                    umma_commit(L.empty(g, m_slot));
-                    if (!RESIDENT) umma_commit(L.b_empty(b_slot));
+                    __syncwarp();
+                    if (!RESIDENT) {
+                        ++b_next;
+                        if (++b_slot == NB) b_slot = 0, b_phase ^= 1u;
+                    }
                 }
-                __syncwarp();
-                trace(trl, 4, tp2, (i << 3) | 2u);
-                if (!RESIDENT) {
-                    ++b_next;
-                    if (++b_slot == NB) b_slot = 0, b_phase ^= 1u;
-                }
-                if (++m_slot == R) m_slot = 0, m_phase ^= 1u;
+                trace(trl, 4, tp2, (f << 3) | 2u);
+                if (++m_slot == F) m_slot = 0, m_phase ^= 1u;
             };
 
+            const uint32_t nf = FILL == 1 ? n : (n + GW - 1) / GW;
             if (!leader) {
-                // gather warp gw takes chunks gw, gw + GW, ...; the ring position of chunk i is (ring_pos + i) mod R
-                uint32_t slot = g_slot + (uint32_t)gw, phase = g_phase;
-                while (slot >= R) slot -= R, phase ^= 1u;
+                // FILL == GW: gather warp gw takes chunk GW f + gw of every fill f (stage GW slot + gw).
+                // FILL == 1:  every chunk is its own fill; warp gw takes fills gw, gw + GW, ...
+                // The ring position of fill f is (g_slot + f) mod F either way.
+                const uint32_t f0 = FILL == 1 ? (uint32_t)gw : 0u, fstep = FILL == 1 ? (uint32_t)GW : 1u;
+                const uint32_t cfill = FILL == 1 ? 0u : (uint32_t)gw;
+                uint32_t slot = g_slot + f0, phase = g_phase;
+                if (slot >= F) slot -= F, phase ^= 1u;
                 int ixa[16], ixb[16];
-                uint32_t i = (uint32_t)gw;
-                if (i < n) load_idx(i, ixa);
-                while (i < n) {
-                    if (i + GW < n) load_idx(i + GW, ixb);
-                    gather(i, ixa, slot, phase);
-                    slot += GW;
-                    while (slot >= R) slot -= R, phase ^= 1u;
-                    i += GW;
-                    if (i >= n) break;
-                    if (i + GW < n) load_idx(i + GW, ixa);
-                    gather(i, ixb, slot, phase);
-                    slot += GW;
-                    while (slot >= R) slot -= R, phase ^= 1u;
-                    i += GW;
+                if ((uint32_t)gw < n) load_idx((uint32_t)gw, ixa);
+                for (uint32_t f = f0; f < nf; f += 2 * fstep) {
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const uint32_t fu = f + (uint32_t)u * fstep;
+                        if (fu >= nf) break;
+                        const uint32_t i = FILL * fu + cfill;             // == gw (mod GW) in both schemes
+                        if (i + GW < n) load_idx(i + GW, u ? ixa : ixb);
+                        trace(trc, 5, tp2, (i << 3) | 0u);
+                        mbar_wait(L.empty(g, slot), phase ^ 1u);
+                        trace(trc, 5, tp2, (i << 3) | 1u);
+                        if (i < n) {
+                            gather(i, u ? ixb : ixa, slot * FILL + cfill);
+                            cp_async_mbar_arrive_noinc(L.full(g, slot));
+                        } else {
+                            mbar_arrive(L.full(g, slot));          // a short last fill: nothing to copy for this warp
+                        }
+                        trace(trc, 5, tp2, (i << 3) | 2u);
+                        slot += fstep;
+                        if (slot >= F) slot -= F, phase ^= 1u;
+                    }
                 }
             } else {
-                // the first warp issues the MMAs in chunk order as the stages fill
-                for (uint32_t i = 0; i < n; ++i) issue(i);
+                for (uint32_t f = 0; f < nf; ++f) issue_fill(f);
             }
-            // ring position of the next tile's first chunk
-            for (uint32_t left = n; left;) {     // (no integer division: n is a few dozen)
-                const uint32_t step = min(left, R - g_slot);
+            // ring position of the next tile's first fill
+            for (uint32_t left = nf; left;) {     // (no integer division: a tile has a few dozen fills at most)
+                const uint32_t step = min(left, F - g_slot);
                 g_slot += step, left -= step;
-                if (g_slot == R) g_slot = 0, g_phase ^= 1u;
+                if (g_slot == F) g_slot = 0, g_phase ^= 1u;
             }
             if (leader) {
                 if (!RESIDENT) skip_to((uint32_t)P.chunks_total);      // release the rest of this round's weight stream
@@ -601,31 +618,39 @@ int conv_fwd_grp(const tl_conv_desc& d, cudaStream_t stream, int nsplit) {
     const uint32_t slab = (uint32_t)n * 64u * nsplit;
     const size_t budget = (size_t)env_int_grp("TL_GRP_SMEM_KB", 224) * 1024;
     const size_t wbytes = (size_t)P.chunks_total * slab;
-    // groups x stages: resident weights if they leave room for at least 2 groups x 3 stages, else a weight ring of >= 4 slabs;
-    // among the feasible (G, R) prefer the most chunks in flight G * (R - 2) (2 stages of a ring are with the tensor core)
+    // Chunks per barrier round trip: one for the narrow layers (most chunks in flight matters: the loaded L2 latency is
+    // ~5000 cycles, profiles/r02_trace_grp_v7_c32.txt), GW for c_out >= 96 (f16) / >= 160 (f16x2) where the MMA warp's per-chunk
+    // hand-off is the bottleneck (profiles/r02_layers_cfg2_f16_grp_v7.txt, r02_grp_v7_fill_f16x2.txt)
+    int fill = (nsplit == 1 ? n >= 96 : n >= 160) ? grp::GW : 1;
+    if (env_int_grp("TL_GRP_FILL", 0) == 1 || env_int_grp("TL_GRP_FILL", 0) == grp::GW) fill = env_int_grp("TL_GRP_FILL", 0);
+    P.fill = fill;
+    const int minR = fill == 1 ? 3 : 2 * fill, maxR = grp::MAX_R / fill * fill;
+    // groups x stages: resident weights if they leave enough room, else a weight ring of >= 4 slabs
     int bestG = 0, bestR = 0, best_res = 0, best_score = -1;
     for (int res = 1; res >= 0; --res) {
         if (res && env_int_grp("TL_GRP_RESIDENT", 1) == 0) continue;
         const size_t bmin = res ? wbytes : (size_t)4 * slab;
         for (int G = grp::MAX_G; G >= 1; --G) {
             if (G * n > grp::TMEM_COLS) continue;
-            for (int R = grp::MAX_R; R >= 3; --R) {
+            if (G > 1 && (G - 1) * sms >= P.num_tiles) continue;     // small levels: spread the tiles over the SMs first
+            for (int R = maxR; R >= minR; R -= fill) {
                 if (grp::smem_bytes(bmin, G, R, stage) > budget) continue;
-                const int score = G * (R - 1 < 4 ? R - 1 : 4);   // stages beyond 5 per group add nothing: 3 gather warps + MMA
+                // fill 1: stages beyond 5 per group add nothing (3 gather warps + MMA); fill GW: whole fills, up to 3
+                const int score = fill == 1 ? G * (R - 1 < 4 ? R - 1 : 4) : G * (R / fill < 3 ? R / fill : 3);
                 if (score > best_score) best_score = score, bestG = G, bestR = R, best_res = res;
                 break;
             }
         }
-        if (best_score >= 9) break;     // resident weights with enough gather depth: take it
+        if (best_score >= (fill == 1 ? 9 : 6)) break;     // resident weights with enough gather depth: take it
     }
     if (env_int_grp("TL_GRP_GROUPS", 0) > 0) {      // experiments: force G, largest R that fits
         bestG = env_int_grp("TL_GRP_GROUPS", 0);
         bestR = 0;
-        for (int R = grp::MAX_R; R >= 2 && !bestR; --R)
+        for (int R = maxR; R >= minR && !bestR; R -= fill)
             if (grp::smem_bytes(best_res ? wbytes : (size_t)4 * slab, bestG, R, stage) <= budget) bestR = R;
     }
-    if (env_int_grp("TL_GRP_R", 0) >= 2 && env_int_grp("TL_GRP_R", 0) <= bestR) bestR = env_int_grp("TL_GRP_R", 0);
-    if (bestG < 1 || bestR < 2 || bestG * n > grp::TMEM_COLS) {
+    if (env_int_grp("TL_GRP_R", 0) >= minR && env_int_grp("TL_GRP_R", 0) <= bestR) bestR = env_int_grp("TL_GRP_R", 0) / fill * fill;
+    if (bestG < 1 || bestR < minR || bestG * n > grp::TMEM_COLS) {
         set_error("tl_conv_fwd(grp): no shared-memory configuration for c_out=%d, %d chunks", n, P.chunks_total);
         return TL_ERR_UNSUPPORTED;
     }
