@@ -90,8 +90,10 @@ def test_conv_linearity_at_full_size(big):
     xh = x.half()
     wh = (w.half()).float()
     ref = sparse.conv([sparse.Seg(xh.float(), wh.contiguous(), lv.nbr, lv.nbr_mask)], lv.n, 64, _lib.MODE_FP32, raw=True)
-    tc = sparse.conv([sparse.Seg(xh, sparse.pack_weight_tc(wh.permute(0, 2, 1), True), lv.nbr, lv.nbr_mask)], lv.n, 64,
-                     _lib.MODE_F16, raw=True)
+    wk = wh.permute(0, 2, 1)                                                   # [K, C_out, C_in]
+    pw = sparse.pack_weight(wk, 1) if sparse.USE_TS else sparse.pack_weight_tc(wk, True)
+    to_k, from_k = (sparse.to_p, sparse.from_p) if sparse.USE_TS else ((lambda a: a), (lambda a: a))   # kernel layout
+    tc = from_k(sparse.conv([sparse.Seg(to_k(xh).contiguous(), pw, lv.nbr, lv.nbr_mask)], lv.n, 64, _lib.MODE_F16, raw=True))
     assert torch.allclose(tc, ref, atol=3e-4, rtol=2e-4)                       # only the accumulation order differs
 
 

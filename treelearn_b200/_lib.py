@@ -77,6 +77,17 @@ SIGNATURES = {
 _lib = None
 
 
+def conv_source_hash():
+    """sha1 over the sparse-conv kernel sources: profiles/*_conv_traffic.json records it so that bench.py can tell whether
+    a committed ncu traffic capture still describes the kernels it is timing."""
+    import hashlib
+    h = hashlib.sha1()
+    for f in ('tl_conv_grp.cu', 'tl_conv_ts.cu', 'tl_conv_tc.cu', 'tl_conv_simt.cu', 'tl_tc_ptx.cuh'):
+        with open(os.path.join(_HERE, 'csrc', f), 'rb') as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
 def load():
     """Load the shared library (once) and bind every declared symbol.  Raises if anything is missing."""
     global _lib
