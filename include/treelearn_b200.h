@@ -61,6 +61,13 @@ int tl_build_level(const uint64_t* fine_keys, int64_t n_fine, const int32_t* fin
  * keys [n] sorted unique -> nbr [27][pad128(n)] i32 (row of voxel at p+delta_k or -1; k = (dx+1)*9+(dy+1)*3+(dz+1)),
  * tile_mask [pad128(n)/128].  hash workspace: tl_rulebook_workspace_bytes(n). */
 size_t tl_rulebook_workspace_bytes(int64_t n);
+/* Per 128-row tile of a submanifold rulebook `nbr` [27][nbr_stride]: the ascending list of DISTINCT neighbour rows
+ * (halo_rows [tiles][cap], halo_cnt [tiles]) and the rulebook rewritten as 16-bit indices into that list (halo_lidx
+ * [tiles][27][128]; 0 = absent).  max_cnt (one int32, zero it first) receives the largest list length; a tile whose list
+ * exceeds `cap` (<= 2048) gets halo_cnt 0 and the caller must not pass the halo to tl_conv_fwd (max_cnt > cap).
+ * New in this library: the reference's spconv gathers pair by pair (no equivalent structure). */
+int tl_halo_build(const int32_t* nbr, int64_t n, int64_t nbr_stride, int32_t cap, int32_t* halo_rows, int32_t* halo_cnt,
+                  uint16_t* halo_lidx, int32_t* max_cnt, void* stream);
 int tl_subm_rulebook(const uint64_t* keys, int64_t n, const int32_t* spatial_shape, int32_t* nbr,
                      uint32_t* tile_mask, void* workspace, size_t workspace_bytes, void* stream);
 
@@ -101,6 +108,14 @@ typedef struct {
     const float* scale2;
     const float* shift2;
     float* splitk_ws; /* optional [n_out, c_out] fp32 scratch: lets layers with few row tiles run split-K */
+    /* optional (modes 2/3, every segment a 27-offset submanifold segment over the SAME rulebook): the level's halo lists
+     * from tl_halo_build.  With them the conv fetches each distinct neighbour row of a 128-row tile once into shared
+     * memory (csrc/tl_conv_halo.cu).  halo_umax = largest halo_cnt of the level (must be <= halo_cap). */
+    const int32_t* halo_rows;  /* [tiles][halo_cap] */
+    const int32_t* halo_cnt;   /* [tiles] */
+    const uint16_t* halo_lidx; /* [tiles][27][128]: 0 = absent, i = halo_rows[tile][i - 1] */
+    int32_t halo_cap;
+    int32_t halo_umax;
 } tl_conv_desc;
 
 #define TL_MODE_FP32 0

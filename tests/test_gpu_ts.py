@@ -55,7 +55,7 @@ def test_ts_subm_conv_parity(nsplit, ci, co):
         assert torch.allclose(sparse.from_p(act.float()).cpu().double(), a1, atol=3e-3, rtol=2e-3)      # + fp16 rounding of the store
         assert torch.allclose(sparse.from_p(act2.float()).cpu().double(), a2, atol=3e-3, rtol=2e-3)
     else:
-        assert torch.allclose(sparse.from_split(act).cpu().double(), a1, **X2_TOL)
+        assert torch.allclose(sparse.from_split(act).cpu().double(), a1, atol=1.2e-4, rtol=6e-5)    # scale up to 1.5 on the raw error
         assert torch.allclose(sparse.from_split(act2).cpu().double(), a2, atol=4e-4, rtol=6e-5)   # scale up to ~5 amplifies the raw error
 
 

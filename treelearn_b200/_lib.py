@@ -28,7 +28,9 @@ class ConvDesc(C.Structure):
     _fields_ = [('n_out', C.c_int32), ('c_out', C.c_int32), ('n_seg', C.c_int32), ('src_fp32_mask', C.c_int32),
                 ('seg', ConvSeg * TL_MAX_SEG), ('residual', C.c_void_p), ('out_raw', C.c_void_p),
                 ('out_act1', C.c_void_p), ('scale1', C.c_void_p), ('shift1', C.c_void_p),
-                ('out_act2', C.c_void_p), ('scale2', C.c_void_p), ('shift2', C.c_void_p), ('splitk_ws', C.c_void_p)]
+                ('out_act2', C.c_void_p), ('scale2', C.c_void_p), ('shift2', C.c_void_p), ('splitk_ws', C.c_void_p),
+                ('halo_rows', C.c_void_p), ('halo_cnt', C.c_void_p), ('halo_lidx', C.c_void_p), ('halo_cap', C.c_int32),
+                ('halo_umax', C.c_int32)]
 
 
 _P, _I32, _I64, _F, _D, _SZ = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double, C.c_size_t
@@ -47,6 +49,7 @@ SIGNATURES = {
     'tl_build_level': (C.c_int, [_P, _I64, _I32P, _P, _P, _P, _P, _P, _P, _I32P, _I64P, _P, _SZ, _P]),
     'tl_rulebook_workspace_bytes': (_SZ, [_I64]),
     'tl_subm_rulebook': (C.c_int, [_P, _I64, _I32P, _P, _P, _P, _SZ, _P]),
+    'tl_halo_build': (C.c_int, [_P, _I64, _I64, _I32, _P, _P, _P, _P, _P]),
     'tl_conv_fwd': (C.c_int, [C.POINTER(ConvDesc), _I32, _P]),
     'tl_heads_fwd': (C.c_int, [_P, _I32, _P, _I64, _I32] + [_P] * 8 + [_P, _P, _P, _P]),
     'tl_merge_workspace_bytes': (_SZ, [_I64]),
@@ -82,7 +85,7 @@ def conv_source_hash():
     a committed ncu traffic capture still describes the kernels it is timing."""
     import hashlib
     h = hashlib.sha1()
-    for f in ('tl_conv_grp.cu', 'tl_conv_ts.cu', 'tl_conv_tc.cu', 'tl_conv_simt.cu', 'tl_tc_ptx.cuh'):
+    for f in ('tl_conv_halo.cu', 'tl_conv_grp.cu', 'tl_conv_ts.cu', 'tl_conv_tc.cu', 'tl_conv_simt.cu', 'tl_tc_ptx.cuh'):
         with open(os.path.join(_HERE, 'csrc', f), 'rb') as fh:
             h.update(fh.read())
     return h.hexdigest()

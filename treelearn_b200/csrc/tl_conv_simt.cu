@@ -130,6 +130,8 @@ bool conv_ts_eligible(const tl_conv_desc& d);                            // tl_c
 int conv_fwd_ts(const tl_conv_desc& d, cudaStream_t stream, int nsplit, uint32_t src_fp32_mask);
 bool conv_grp_eligible(const tl_conv_desc& d, uint32_t src_fp32_mask);   // tl_conv_grp.cu
 int conv_fwd_grp(const tl_conv_desc& d, cudaStream_t stream, int nsplit);
+bool conv_halo_eligible(const tl_conv_desc& d, uint32_t src_fp32_mask);  // tl_conv_halo.cu
+int conv_fwd_halo(const tl_conv_desc& d, cudaStream_t stream, int nsplit);
 
 // ------------------------------------------------------------------------------------------------
 // voxel -> point gather + both MLP heads, one thread per point, weights broadcast from smem
@@ -279,6 +281,10 @@ int tl_conv_fwd(const tl_conv_desc* desc, int32_t mode, void* stream_) {
         // (tl_conv_ts.cu); 0 round 1's kernel (natural channel order)
         static const int use_ts = getenv("TL_TS") ? atoi(getenv("TL_TS")) : 1;
         if (in4) return conv_fwd_in4(d, stream, 2, use_ts != 0);      // the 4-channel network input is always fp32
+        if (use_ts == 1 && conv_halo_eligible(d, (uint32_t)d.src_fp32_mask)) {      // submanifold conv with the level's halo lists
+            const int rc = conv_fwd_halo(d, stream, 1);
+            if (rc != TL_ERR_UNSUPPORTED) return rc;
+        }
         if (use_ts == 1 && conv_grp_eligible(d, (uint32_t)d.src_fp32_mask)) return conv_fwd_grp(d, stream, 1);
         if (use_ts && conv_ts_eligible(d)) return conv_fwd_ts(d, stream, 1, (uint32_t)d.src_fp32_mask);
         TL_REQUIRE(d.src_fp32_mask == 0, "tl_conv_fwd(f16): fp32 segment sources need the tensor-memory path");
@@ -287,6 +293,10 @@ int tl_conv_fwd(const tl_conv_desc* desc, int32_t mode, void* stream_) {
     if (mode == TL_MODE_F16X2) {
         static const int use_ts2 = getenv("TL_TS") ? atoi(getenv("TL_TS")) : 1;
         if (in4) return conv_fwd_in4(d, stream, 22, true);
+        if (use_ts2 == 1 && conv_halo_eligible(d, (uint32_t)d.src_fp32_mask)) {
+            const int rc = conv_fwd_halo(d, stream, 2);
+            if (rc != TL_ERR_UNSUPPORTED) return rc;
+        }
         if (use_ts2 == 1 && conv_grp_eligible(d, (uint32_t)d.src_fp32_mask)) return conv_fwd_grp(d, stream, 2);
         if (!conv_ts_eligible(d)) {
             set_error("tl_conv_fwd(f16x2): shape not eligible (c_in %% 32, c_out %% 32, <= 256 channels)");

@@ -143,10 +143,18 @@ class LazyLevels:
             _extend_levels(self.levels, self.num_levels)
             for lv in self.levels[1:]:
                 build_subm_rulebook(lv)
+            for lv in self.levels[1:]:      # one host read per level, on the side stream: the main stream keeps running
+                h = getattr(lv.nbr, 'halo', None)
+                if h is not None:
+                    h.umax
         main.wait_stream(side)
         for lv in self.levels:        # tensors allocated under the side stream are consumed by main-stream kernels
             for t in (lv.keys, lv.coords, lv.nbr, lv.nbr_mask, lv.down_index, lv.down_mask, lv.up_index, lv.up_mask):
                 if t is not None:
+                    t.record_stream(main)
+            h = getattr(lv.nbr, 'halo', None) if lv.nbr is not None else None
+            if h is not None:
+                for t in (h.rows, h.cnt, h.lidx):
                     t.record_stream(main)
 
     def __len__(self):
@@ -174,7 +182,41 @@ def build_subm_rulebook(lv):
     ws = _workspace(wsb, dev)
     shape = (C.c_int32 * 3)(*lv.shape)
     check(lib.tl_subm_rulebook(ptr(lv.keys), lv.n, shape, ptr(lv.nbr), ptr(lv.nbr_mask), ptr(ws), wsb, stream_ptr()))
+    if USE_HALO:
+        build_halo(lv)
     return lv
+
+
+class Halo:
+    """Per 128-row tile of a level: the distinct neighbour rows and the 3^3 rulebook as 16-bit indices into that list
+    (tl_halo_build, csrc/tl_conv_halo.cu).  Hangs off the level's `nbr` tensor so that sparse.conv finds it from the
+    segments' index tensors.  `umax` (largest list of the level) costs one host read of an int32."""
+
+    def __init__(self, rows, cnt, lidx, max_cnt, cap):
+        self.rows, self.cnt, self.lidx, self.max_cnt, self.cap, self._umax = rows, cnt, lidx, max_cnt, cap, None
+
+    @property
+    def umax(self):
+        if self._umax is None:
+            self._umax = int(self.max_cnt.item())
+        return self._umax
+
+    @property
+    def usable(self):
+        return 0 < self.umax <= self.cap
+
+
+def build_halo(lv, cap=None):
+    lib = _lib.load()
+    dev = lv.keys.device
+    cap = cap or HALO_CAP
+    tiles = pad_rows(lv.n) // TILE_ROWS
+    h = Halo(torch.empty((tiles, cap), dtype=torch.int32, device=dev), torch.empty(tiles, dtype=torch.int32, device=dev),
+             torch.empty((tiles, 27, TILE_ROWS), dtype=torch.int16, device=dev), torch.zeros(1, dtype=torch.int32, device=dev), cap)
+    check(lib.tl_halo_build(ptr(lv.nbr), lv.n, lv.nbr.stride(0), cap, ptr(h.rows), ptr(h.cnt), ptr(h.lidx), ptr(h.max_cnt),
+                            stream_ptr()))
+    lv.nbr.halo = h
+    return h
 
 
 # ---- segmented gather-GEMM convolution -----------------------------------------------------------
@@ -216,6 +258,9 @@ def pack_weight_tc(w, half, bk=None):
 # TL_TS: 1 (default) group kernel csrc/tl_conv_grp.cu; 2 tensor-memory-A kernel csrc/tl_conv_ts.cu; 0 round-1 kernel (natural layout)
 TS_KIND = int(os.environ.get('TL_TS', '1'))
 USE_TS = TS_KIND != 0
+# halo-cached submanifold conv (csrc/tl_conv_halo.cu) behind the group kernel's modes; TL_HALO=0 turns it off
+USE_HALO = TS_KIND == 1 and os.environ.get('TL_HALO', '1') != '0'
+HALO_CAP = int(os.environ.get('TL_HALO_CAP', '512'))
 
 
 # ---- "P-layout" of the tensor-memory-A kernel (csrc/tl_conv_ts.cu) -----------------------------------------------------
@@ -336,6 +381,10 @@ def conv(segs, n_out, c_out, mode, residual=None, raw=False, act1=None, act2=Non
         g.weight, g.n_off = ptr(s.weight), s.weight.shape[0]
         if s.index is not None:
             g.index, g.index_stride, g.tile_mask = ptr(s.index), s.index.stride(0), ptr(s.mask)
+    halo = getattr(segs[0].index, 'halo', None) if (mode in half_modes and not d.src_fp32_mask) else None
+    if halo is not None and all(sg.index is segs[0].index for sg in segs) and halo.usable:
+        d.halo_rows, d.halo_cnt, d.halo_lidx = ptr(halo.rows), ptr(halo.cnt), ptr(halo.lidx)
+        d.halo_cap, d.halo_umax = halo.cap, halo.umax
     outs = []
     d.residual = ptr(residual)
     act_dtype = torch.float16 if mode in half_modes else torch.float32   # operand format of the consumers
