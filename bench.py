@@ -169,6 +169,77 @@ def plot_record(net, args, world, rank, dev, dist):
     return rec
 
 
+def train_record(args, world, rank, dev, dist):
+    """BASELINE.json configs 3 and 5 -- the training step of tools/training/train.py:32-44 (forward + loss under fp16
+    autocast, GradScaler, backward, gradient clip, AdamW) through `treelearn_b200.dist.train_step`, batches in pinned HOST
+    memory.  cfg3 (1 GPU only): one 4-tile batch.  cfg5: data parallel, 2 tiles per GPU, level-bucketed NCCL all-reduce
+    launched from backward hooks (weak scaling: voxels/s summed over the ranks, time = max over ranks)."""
+    from treelearn_b200 import TreeLearn, synth, sparse
+    from treelearn_b200 import dist as tdist
+
+    def run(n_tiles, seed0, steps=4, warmup=2):
+        tiles = [synth.synth_forest(edge=20.0, n_trees=20, seed=seed0 + s) for s in range(n_tiles)]
+        batch = synth.make_batch(tiles)
+        batch = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in batch.items()}
+        with torch.no_grad():
+            _, vc, _, _ = sparse.voxelize(batch['coords'].to(dev), batch['input_feats'].to(dev), batch['batch_ids'].to(dev),
+                                          n_tiles, 0.1, False, False, 3)
+        n_vox = torch.tensor([float(vc.shape[0])], device=dev, dtype=torch.float64)
+        torch.manual_seed(0)
+        net = TreeLearn(mode='tf32', **MODEL_CFG).to(dev).train()
+        opt = torch.optim.AdamW(net.parameters(), lr=2e-3, weight_decay=1e-3)
+        scaler = torch.amp.GradScaler('cuda')
+        red = tdist.OverlappedGradReducer(net)
+        exposed = []
+        finish = red.finish
+
+        def timed_finish():            # device time between the end of backward and the end of the last all-reduce
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            finish()
+            b.record()
+            exposed.append((a, b))
+        red.finish = timed_finish
+        for _ in range(warmup):
+            tdist.train_step(net, opt, batch, reducer=red, scaler=scaler, autocast=True, grad_clip=10.0)
+        exposed.clear()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            loss, _ = tdist.train_step(net, opt, batch, reducer=red, scaler=scaler, autocast=True, grad_clip=10.0)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1) / steps, sum(a.elapsed_time(b) for a, b in exposed) / steps], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            dist.all_reduce(n_vox)
+        red.remove()
+        ms_step, ms_exposed = ms.tolist()
+        out = {'tiles_per_gpu': n_tiles, 'voxels_total': int(n_vox.item()), 'ms_per_step': round(ms_step, 2),
+               'Mvoxels_per_s': round(n_vox.item() / (ms_step * 1e-3) / 1e6, 2), 'loss': round(float(loss.item()), 4),
+               'steps': steps, 'warmup': warmup, 'peak_mem_GiB': round(torch.cuda.max_memory_allocated() / 2 ** 30, 1)}
+        if world > 1:
+            out['allreduce_exposed_ms'] = round(ms_exposed, 2)
+        del net, opt
+        torch.cuda.empty_cache()
+        return out
+
+    rec = {'step': 'treelearn_b200.dist.train_step: fp16 autocast + GradScaler (tools/training/train.py:32-44), TF32 tcgen05 '
+                   'conv forward / data-gradient kernels, TF32 weight gradients, batch-statistics BatchNorm, clip 10, AdamW; '
+                   'random-init default U-Net, 20 m synthetic tiles, host batches',
+           'n_gpus': world}
+    if world == 1:
+        rec['cfg3_4tile_batch'] = run(4, 0)
+    rec['cfg5_dp_2tiles_per_gpu'] = dict(run(2, 10 * rank), scaling='weak',
+                                         allreduce='one NCCL all-reduce per U-Net level bucket, launched from backward hooks')
+    return rec
+
+
 # ----------------------------------------------------------------------------------------------------
 DTYPE_TEXT = {
     'fp32': 'f32',
@@ -358,6 +429,7 @@ def run_b200(args):
 
     cluster = cluster_record(args, resident, dev) if (rank == 0 and not args.no_cluster) else None
     plot = None if args.no_plot else plot_record(raw_net, args, world, rank, dev, dist)
+    train = None if args.no_train else train_record(args, world, rank, dev, dist)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -387,6 +459,8 @@ def run_b200(args):
         line['cluster_trained_like'] = cluster
     if plot is not None:
         line['plot'] = plot
+    if train is not None:
+        line['train'] = train
     if world == 1 and not args.no_cpu_baseline:
         line['cpu_baseline'], line['parity'] = cpu_baseline_and_parity(make_net, sd_cpu, fit_tile, args.mode, budget_s=20.0)
     print(json.dumps(line), flush=True)
@@ -533,6 +607,7 @@ if __name__ == '__main__':
     ap.add_argument('--mode', default='f16x2', choices=['fp32', 'tf32', 'f16', 'f16x2'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-cluster', action='store_true', help='skip the trained-like clustering record')
+    ap.add_argument('--no-train', action='store_true', help='skip the cfg-3 / cfg-5 training-step record')
     ap.add_argument('--no-plot', action='store_true', help='skip the cfg-4 whole-plot (strong scaling) record')
     a = ap.parse_args()
     if a.impl == 'reference':

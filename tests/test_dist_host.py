@@ -90,3 +90,66 @@ def test_grad_buckets_cover_trainable_parameters_once():
     want = [id(p) for p in net.parameters() if p.requires_grad]
     assert sorted(flat) == sorted(want) and len(set(flat)) == len(flat)
     assert len(buckets) == 5                                   # 4 U-Net levels + the non-U-Net bucket
+
+
+class _Toy(torch.nn.Module):
+    """Parameter names shaped like the U-Net's (`unet.` + one `.u.` hop per level) so grad_buckets splits them by level."""
+
+    def __init__(self):
+        super().__init__()
+        lin = lambda: torch.nn.Linear(4, 4)   # noqa: E731
+        self.input_conv = lin()
+        self.unet = torch.nn.Module()
+        self.unet.blocks = lin()
+        self.unet.u = torch.nn.Module()
+        self.unet.u.blocks = lin()
+        self.unet.u.unused = lin()            # never used in forward: its gradient stays None (= zeros in the bucket)
+        self.unet.blocks_tail = lin()
+
+    def forward(self, x):
+        x = self.unet.blocks(self.input_conv(x))
+        return self.unet.blocks_tail(x + self.unet.u.blocks(x)).sum()
+
+
+def _overlap_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from treelearn_b200.dist import OverlappedGradReducer
+    torch.manual_seed(0)
+    a, b = _Toy(), _Toy()
+    b.load_state_dict(a.state_dict())
+    x = torch.randn(5, 4, generator=torch.Generator().manual_seed(10 + rank))
+    red = OverlappedGradReducer(a)
+    ok = True
+    for it in range(2):                       # two steps: the reducer resets itself
+        for m in (a, b):
+            for p in m.parameters():
+                p.grad = None
+        a(x).backward()
+        launched = red.launched_in_backward
+        red.finish()
+        b(x).backward()
+        allreduce_grads(b)
+        # the level-1 bucket holds the unused layer, so it can only be launched by finish(); the other two complete in backward
+        ok &= launched == 2
+        for (n, p), (_, r) in zip(a.named_parameters(), b.named_parameters()):
+            ok &= p.grad is not None and bool(torch.allclose(p.grad, r.grad, rtol=0, atol=1e-7))
+            if 'unused' in n:
+                ok &= bool((p.grad == 0).all())
+    red.remove()
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_overlapped_grad_reducer_matches_allreduce_grads_gloo_world2():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 33500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_overlap_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == [(0, True), (1, True)]

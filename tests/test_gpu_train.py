@@ -230,3 +230,54 @@ def test_frozen_modules_and_optimizer_step():
             assert torch.equal(before[k], after[k]), k        # frozen weights AND frozen BN running stats
     loss1, _ = net(batch, return_loss=True)
     assert loss1.item() != loss0.item()
+
+
+def test_training_step_under_fp16_autocast_and_gradscaler():
+    """The reference trains under `torch.cuda.amp.autocast` (fp16) with a GradScaler (tools/training/train.py:32-44,118).
+    The drop-in model must run unchanged under that context: the conv / BatchNorm kernels keep their own arithmetic
+    (fp32 or TF32 operands, fp32 accumulate: at least the precision autocast gives spconv), the torch heads run in fp16,
+    the loss casts back to fp32 (tree_learn.py:111-112).  Loss and gradients stay close to the plain fp32 step, the
+    scaler unscales finite gradients and AdamW moves the parameters."""
+    from treelearn_b200 import dist as tdist
+    batch = synth.make_batch([synth.synth_forest(edge=5.0, n_trees=3, seed=3, ground_density=150.0)], inner_edge=3.0)
+    sd = model_ref.make_state_dict(channels=32, num_blocks=4, seed=2)
+
+    def make():
+        net = TreeLearn(channels=32, num_blocks=4, use_feats=False, use_coords=False, spatial_shape=[500, 500, 1000], mode='tf32')
+        net.load_state_dict(sd)
+        return net.cuda().train()
+
+    plain = make()
+    loss_p, _ = plain(batch, return_loss=True)
+    loss_p.backward()
+    # the reference loop, literally
+    net = make()
+    before = {n: p.detach().clone() for n, p in net.named_parameters()}
+    optimizer = torch.optim.AdamW(net.parameters(), lr=1e-3, weight_decay=1e-3)
+    scaler = torch.amp.GradScaler('cuda', enabled=True)
+    with torch.autocast('cuda', dtype=torch.float16, enabled=True):
+        loss, loss_dict = net(batch, return_loss=True)
+    assert loss.dtype == torch.float32 and set(loss_dict) == {'semantic_loss', 'offset_loss'}
+    assert all(np.isfinite(v.detach().cpu().item()) for v in loss_dict.values())
+    optimizer.zero_grad()
+    scaler.scale(loss).backward()
+    scaler.unscale_(optimizer)
+    torch.nn.utils.clip_grad_norm_(net.parameters(), 1e9)
+    grads = {n: p.grad.clone() for n, p in net.named_parameters()}
+    scaler.step(optimizer)
+    scaler.update()
+    assert abs(loss.item() - loss_p.item()) < 2e-2 * max(abs(loss_p.item()), 1.0), (loss.item(), loss_p.item())
+    assert all(torch.isfinite(g).all() for g in grads.values())
+    names = [n for n, p in plain.named_parameters() if p.grad.abs().max().item() >= 1e-6]
+    a = torch.cat([grads[n].flatten() for n in names])
+    b = torch.cat([dict(plain.named_parameters())[n].grad.flatten() for n in names])
+    cos = F.cosine_similarity(a, b, dim=0).item()
+    print(f'autocast(fp16)+GradScaler vs plain step: loss {loss.item():.5f} vs {loss_p.item():.5f}, gradient cosine {cos:.5f}')
+    assert cos > 0.99, cos
+    moved = sum(int(not torch.equal(before[n], p.detach())) for n, p in net.named_parameters())
+    assert moved > 0.9 * len(before)
+    # the library's own step helper takes the same route
+    net2 = make()
+    opt2 = torch.optim.AdamW(net2.parameters(), lr=1e-3, weight_decay=1e-3)
+    l2, _ = tdist.train_step(net2, opt2, batch, scaler=torch.amp.GradScaler('cuda'), autocast=True, grad_clip=1e9)
+    assert abs(l2.item() - loss.item()) < 1e-2 * max(abs(loss.item()), 1.0)

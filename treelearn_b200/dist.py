@@ -141,15 +141,97 @@ def allreduce_grads(model, group=None):
             off += n
 
 
-def train_step(model, optimizer, batch, group=None, grad_clip=None):
-    """One data-parallel training step on this rank's batch (tools/training/train.py:32-44 without AMP):
-    forward + loss, backward, gradient all-reduce, optional clip, optimizer step.  Returns (loss, loss_dict)."""
+class OverlappedGradReducer:
+    """Gradient all-reduce launched DURING backward (SURVEY §8e training row): every parameter carries a
+    post-accumulate-grad hook; when the last gradient of a bucket (one U-Net level, `grad_buckets`) has been written the
+    bucket is flattened and its all-reduce(sum) starts asynchronously on the communicator's stream while autograd keeps
+    running the shallower levels' data- and weight-gradient kernels.  Backward reaches the deepest level first on the way
+    down the decoder side and finishes level 0 last, so only the last bucket's transfer is exposed.
+    `finish()` launches whatever never completed (parameters without a gradient count as zeros), waits, scales by 1/world
+    and writes the averages back into `.grad`.  With world == 1 (or no process group) it does nothing."""
+
+    def __init__(self, model, group=None):
+        self.group = group
+        self.active = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        self.world = dist.get_world_size(group) if self.active else 1
+        self.buckets = grad_buckets(model)
+        self._where = {}
+        self._handles = []
+        for b, params in enumerate(self.buckets):
+            for p in params:
+                self._where[id(p)] = b
+                if self.active:
+                    self._handles.append(p.register_post_accumulate_grad_hook(self._hook))
+        self.reset()
+
+    def reset(self):
+        self._ready = [0] * len(self.buckets)
+        self._pending = [None] * len(self.buckets)
+        self.launched_in_backward = 0
+
+    def _launch(self, b):
+        params = self.buckets[b]
+        flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in params])
+        self._pending[b] = (dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True), flat)
+
+    def _hook(self, p):
+        b = self._where[id(p)]
+        self._ready[b] += 1
+        if self._ready[b] == len(self.buckets[b]) and self._pending[b] is None:
+            self._launch(b)
+            self.launched_in_backward += 1
+
+    def finish(self):
+        if not self.active:
+            return
+        for b in range(len(self.buckets)):
+            if self._pending[b] is None:
+                self._launch(b)
+        for b, params in enumerate(self.buckets):
+            work, flat = self._pending[b]
+            work.wait()
+            flat.mul_(1.0 / self.world)
+            off = 0
+            for p in params:
+                n = p.numel()
+                g = flat[off:off + n].view_as(p)
+                if p.grad is None:
+                    p.grad = g.clone()
+                else:
+                    p.grad.copy_(g)
+                off += n
+        self.reset()
+
+    def remove(self):
+        for h in self._handles:
+            h.remove()
+        self._handles = []
+
+
+def train_step(model, optimizer, batch, group=None, grad_clip=None, reducer=None, scaler=None, autocast=False):
+    """One data-parallel training step on this rank's batch (tools/training/train.py:32-44): forward + loss (optionally
+    under fp16 autocast with a GradScaler, as the reference trains), backward with the bucketed gradient all-reduce
+    overlapped (`reducer`, an OverlappedGradReducer; None = all-reduce after backward), optional clip, optimizer step.
+    Returns (loss, loss_dict)."""
     model.train()
     optimizer.zero_grad(set_to_none=True)
-    loss, loss_dict = model(batch, return_loss=True)
-    loss.backward()
-    allreduce_grads(model, group)
+    with torch.autocast('cuda', dtype=torch.float16, enabled=bool(autocast)):
+        loss, loss_dict = model(batch, return_loss=True)
+    if scaler is not None:
+        scaler.scale(loss).backward()
+    else:
+        loss.backward()
+    if reducer is not None:
+        reducer.finish()
+    else:
+        allreduce_grads(model, group)
+    if scaler is not None:
+        scaler.unscale_(optimizer)
     if grad_clip:
         torch.nn.utils.clip_grad_norm_([p for p in model.parameters() if p.requires_grad], grad_clip)
-    optimizer.step()
+    if scaler is not None:
+        scaler.step(optimizer)
+        scaler.update()
+    else:
+        optimizer.step()
     return loss.detach(), {k: v.detach() for k, v in loss_dict.items()}
