@@ -207,11 +207,15 @@ def train_record(args, world, rank, dev, dist):
         if world > 1:
             dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = [e0]
         e0.record()
         for _ in range(steps):
             loss, _ = tdist.train_step(net, opt, batch, reducer=red, scaler=scaler, autocast=True, grad_clip=10.0)
+            marks.append(torch.cuda.Event(enable_timing=True))
+            marks[-1].record()
         e1.record()
         torch.cuda.synchronize()
+        per_step = [round(a.elapsed_time(b), 1) for a, b in zip(marks[:-1], marks[1:])]
         if world > 1:
             dist.barrier()
         ms = torch.tensor([e0.elapsed_time(e1) / steps, sum(a.elapsed_time(b) for a, b in exposed) / steps], device=dev)
@@ -222,7 +226,8 @@ def train_record(args, world, rank, dev, dist):
         ms_step, ms_exposed = ms.tolist()
         out = {'tiles_per_gpu': n_tiles, 'voxels_total': int(n_vox.item()), 'ms_per_step': round(ms_step, 2),
                'Mvoxels_per_s': round(n_vox.item() / (ms_step * 1e-3) / 1e6, 2), 'loss': round(float(loss.item()), 4),
-               'steps': steps, 'warmup': warmup, 'peak_mem_GiB': round(torch.cuda.max_memory_allocated() / 2 ** 30, 1)}
+               'steps': steps, 'warmup': warmup, 'ms_each_step': per_step, 'grad_scale': float(scaler.get_scale()),
+               'peak_mem_GiB': round(torch.cuda.max_memory_allocated() / 2 ** 30, 1)}
         if world > 1:
             out['allreduce_exposed_ms'] = round(ms_exposed, 2)
         del net, opt

@@ -61,13 +61,19 @@ int tl_build_level(const uint64_t* fine_keys, int64_t n_fine, const int32_t* fin
  * keys [n] sorted unique -> nbr [27][pad128(n)] i32 (row of voxel at p+delta_k or -1; k = (dx+1)*9+(dy+1)*3+(dz+1)),
  * tile_mask [pad128(n)/128].  hash workspace: tl_rulebook_workspace_bytes(n). */
 size_t tl_rulebook_workspace_bytes(int64_t n);
-/* Per 128-row tile of a submanifold rulebook `nbr` [27][nbr_stride]: the ascending list of DISTINCT neighbour rows
- * (halo_rows [tiles][cap], halo_cnt [tiles]) and the rulebook rewritten as 16-bit indices into that list (halo_lidx
- * [tiles][27][128]; 0 = absent).  max_cnt (one int32, zero it first) receives the largest list length; a tile whose list
- * exceeds `cap` (<= 2048) gets halo_cnt 0 and the caller must not pass the halo to tl_conv_fwd (max_cnt > cap).
- * New in this library: the reference's spconv gathers pair by pair (no equivalent structure). */
-int tl_halo_build(const int32_t* nbr, int64_t n, int64_t nbr_stride, int32_t cap, int32_t* halo_rows, int32_t* halo_cnt,
-                  uint16_t* halo_lidx, int32_t* max_cnt, void* stream);
+/* Per 128-row tile of a submanifold rulebook `nbr` [27][nbr_stride] over the Morton keys `keys` [n]: the list of DISTINCT
+ * neighbour rows and the rulebook rewritten as 16-bit entries into that list, laid out so that the conv kernel's
+ * shared-memory reads are bank-conflict free (csrc/tl_conv_halo.cu, "class swizzle"):
+ *   halo_rows [tiles][cap]     entry p - 1 = row id | cls << 28 for list position p >= 1, -1 = unused position
+ *                              (cls = keys[row] & 7, the voxel's parity class; p is odd iff cls bit 2 is set)
+ *   halo_cnt  [tiles]          positions in use (0 when the tile's list exceeds `cap`)
+ *   halo_lidx [tiles][28][128] rows 0..26: per LANE, position | cls << 13 of the neighbour at offset k (0 = absent);
+ *                              row 27: the tile row each lane holds (the rows of a tile are permuted over the lanes so that
+ *                              the 8 lanes of a shared-memory phase carry 8 different classes)
+ * max_cnt (one int32, zero it first) receives the largest halo_cnt; if it exceeds `cap` (<= 2048) the caller must not pass
+ * the halo to tl_conv_fwd.  New in this library: the reference's spconv gathers pair by pair (no equivalent structure). */
+int tl_halo_build(const int32_t* nbr, const uint64_t* keys, int64_t n, int64_t nbr_stride, int32_t cap, int32_t* halo_rows,
+                  int32_t* halo_cnt, uint16_t* halo_lidx, int32_t* max_cnt, void* stream);
 int tl_subm_rulebook(const uint64_t* keys, int64_t n, const int32_t* spatial_shape, int32_t* nbr,
                      uint32_t* tile_mask, void* workspace, size_t workspace_bytes, void* stream);
 
@@ -113,7 +119,7 @@ typedef struct {
      * memory (csrc/tl_conv_halo.cu).  halo_umax = largest halo_cnt of the level (must be <= halo_cap). */
     const int32_t* halo_rows;  /* [tiles][halo_cap] */
     const int32_t* halo_cnt;   /* [tiles] */
-    const uint16_t* halo_lidx; /* [tiles][27][128]: 0 = absent, i = halo_rows[tile][i - 1] */
+    const uint16_t* halo_lidx; /* [tiles][28][128], see tl_halo_build */
     int32_t halo_cap;
     int32_t halo_umax;
 } tl_conv_desc;
@@ -217,6 +223,15 @@ int tl_pack_weight_tc(const float* w, int32_t c_out, int32_t n_off, int32_t c_in
 int tl_conv_wgrad(const float* src, int64_t src_stride, int32_t c_in, int32_t n_off, const int32_t* index,
                   int64_t index_stride, const uint32_t* tile_mask, const float* d_out, int64_t n_out, int32_t c_out,
                   float* dw, int32_t tf32, void* stream);
+/* The same weight gradient on the tcgen05 tensor cores (TF32 operands = the upper 19 bits of the fp32 inputs, fp32
+ * accumulate in tensor memory; csrc/tl_wgrad_tc.cu) for C_in % 32 == 0, C_out % 32 == 0, C_out <= 256
+ * (tl_conv_wgrad_tc_eligible).  Replaces spconv's implicit-GEMM wgrad reached through autograd at
+ * tools/training/train.py:40.  Per-CTA partial sums in `workspace` are added in a fixed order: run-to-run deterministic. */
+int tl_conv_wgrad_tc_eligible(int32_t c_in, int32_t c_out);
+size_t tl_conv_wgrad_tc_workspace_bytes(int64_t n_out, int32_t c_in, int32_t n_off, int32_t c_out);
+int tl_conv_wgrad_tc(const float* src, int64_t src_stride, int32_t c_in, int32_t n_off, const int32_t* index,
+                     int64_t index_stride, const uint32_t* tile_mask, const float* d_out, int64_t n_out, int32_t c_out,
+                     float* dw, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- after the path -----------------------------------------------------------
  * tl_hash_join_last: exact-coordinate join, replaces the Python `hash(tuple(point))` dictionaries of

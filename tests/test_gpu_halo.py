@@ -22,26 +22,56 @@ def _level(edge=8.0, seed=11):
 
 
 def test_halo_lists_match_numpy():
+    """The lists against numpy: the distinct neighbour rows of every tile, each at a position whose parity is bit 2 of its
+    parity class; the rulebook as (position | class << 13) per LANE with the lane -> row permutation in row 27; and the
+    purpose of it all -- within every 8-lane shared-memory phase the live entries of an offset carry different classes
+    (= different bank groups) except where a tile holds more than 16 rows of one class."""
     lv = _level()
     h = lv.nbr.halo
     assert h.usable and h.umax <= h.cap
     nbr = lv.nbr.cpu().numpy()[:, :lv.n]
+    keys = lv.keys.cpu().numpy()
     rows, cnt, lidx = h.rows.cpu().numpy(), h.cnt.cpu().numpy(), h.lidx.cpu().numpy().astype(np.int64) & 0xffff
     tiles = (lv.n + 127) // 128
     assert tiles > 3 and lv.n % 128 != 0            # several tiles, ragged last one
     umax = 0
+    live_total = clash_total = natural_clash = 0
     for t in range(tiles):
         blk = nbr[:, t * 128:(t + 1) * 128]
+        ncols = blk.shape[1]
         want = np.unique(blk[blk >= 0])
-        umax = max(umax, len(want))
-        assert cnt[t] == len(want)
-        assert np.array_equal(rows[t, :cnt[t]], want)                       # ascending, distinct
-        got = lidx[t][:, :blk.shape[1]]
-        assert np.array_equal(got == 0, blk < 0)                            # 0 <=> absent neighbour
-        live = blk >= 0
-        assert np.array_equal(rows[t][got[live] - 1], blk[live])            # index i -> halo row i - 1
-        assert (lidx[t][:, blk.shape[1]:] == 0).all()                       # rows past n_out: absent
+        ent = rows[t, :cnt[t]]
+        used = ent[ent >= 0]
+        ids, cls = used & ((1 << 28) - 1), used >> 28
+        assert np.array_equal(np.sort(ids), want)                           # every distinct neighbour row exactly once
+        assert np.array_equal(cls, keys[ids] & 7)                           # tagged with its parity class
+        pos = np.nonzero(ent >= 0)[0] + 1
+        assert np.array_equal(pos & 1, cls >> 2)                            # odd position <=> class bit 2
+        umax = max(umax, int(cnt[t]))
+        perm = lidx[t][27]
+        assert np.array_equal(np.sort(perm), np.arange(128))                # lane -> tile row permutation
+        got = lidx[t][:27]                                                  # [k][lane]
+        p, c = got & 0x1FFF, got >> 13
+        for k in range(27):
+            r = perm                                                        # tile row of every lane
+            inside = r < ncols
+            v = np.where(inside, blk[k, np.minimum(r, ncols - 1)], -1)
+            assert np.array_equal(p[k] == 0, v < 0)                         # 0 <=> absent neighbour (or a row past n_out)
+            live = v >= 0
+            assert np.array_equal(ent[p[k][live] - 1] & ((1 << 28) - 1), v[live])
+            assert np.array_equal(c[k][live], keys[v[live]] & 7)
+            for ph in range(16):                                            # bank-group clashes inside the 8-lane phases
+                sel = live[8 * ph:8 * ph + 8]
+                cc = c[k][8 * ph:8 * ph + 8][sel]
+                live_total += len(cc)
+                clash_total += len(cc) - len(set(cc.tolist()))
+                nat = blk[k, 8 * ph:min(8 * ph + 8, ncols)]
+                nat = keys[nat[nat >= 0]] & 7
+                natural_clash += len(nat) - len(set(nat.tolist()))
     assert h.umax == umax
+    print(f'same-class entries inside a phase: {clash_total} of {live_total} live entries with the lane permutation, '
+          f'{natural_clash} in natural row order')
+    assert clash_total < 0.12 * live_total and clash_total < 0.5 * natural_clash
 
 
 @pytest.mark.parametrize('nsplit', [1, 2])

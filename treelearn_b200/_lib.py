@@ -49,7 +49,7 @@ SIGNATURES = {
     'tl_build_level': (C.c_int, [_P, _I64, _I32P, _P, _P, _P, _P, _P, _P, _I32P, _I64P, _P, _SZ, _P]),
     'tl_rulebook_workspace_bytes': (_SZ, [_I64]),
     'tl_subm_rulebook': (C.c_int, [_P, _I64, _I32P, _P, _P, _P, _SZ, _P]),
-    'tl_halo_build': (C.c_int, [_P, _I64, _I64, _I32, _P, _P, _P, _P, _P]),
+    'tl_halo_build': (C.c_int, [_P, _P, _I64, _I64, _I32, _P, _P, _P, _P, _P]),
     'tl_conv_fwd': (C.c_int, [C.POINTER(ConvDesc), _I32, _P]),
     'tl_heads_fwd': (C.c_int, [_P, _I32, _P, _I64, _I32] + [_P] * 8 + [_P, _P, _P, _P]),
     'tl_merge_workspace_bytes': (_SZ, [_I64]),
@@ -68,6 +68,9 @@ SIGNATURES = {
     'tl_bn_relu_bwd': (C.c_int, [_P, _P, _I64, _I32, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _P]),
     'tl_pack_weight_tc': (C.c_int, [_P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P]),
     'tl_conv_wgrad': (C.c_int, [_P, _I64, _I32, _I32, _P, _I64, _P, _P, _I64, _I32, _P, _I32, _P]),
+    'tl_conv_wgrad_tc_eligible': (C.c_int, [_I32, _I32]),
+    'tl_conv_wgrad_tc_workspace_bytes': (_SZ, [_I64, _I32, _I32, _I32]),
+    'tl_conv_wgrad_tc': (C.c_int, [_P, _I64, _I32, _I32, _P, _I64, _P, _P, _I64, _I32, _P, _P, _SZ, _P]),
     'tl_hash_join_workspace_bytes': (_SZ, [_I64]),
     'tl_hash_join_last': (C.c_int, [_P, _I32, _I32, _P, _I64, _P, _I32, _I32, _I64, _I64, _P, _P, _SZ, _P]),
     'tl_cooccurrence_counts': (C.c_int, [_P, _P, _I64, _I64, _I64, _P, _P]),

@@ -13,6 +13,7 @@ The reference trains by torch autograd through spconv's conv modules and `nn.Bat
   handles them); so does the loss.
 """
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -21,6 +22,10 @@ import torch
 from . import _lib, sparse
 from ._lib import check, ptr, stream_ptr
 from .sparse import Seg
+
+
+# TL_WGRAD_TC=0 falls back to the round-1 mma.sync + atomicAdd weight-gradient kernel (A/B measurements only)
+USE_WGRAD_TC = os.environ.get('TL_WGRAD_TC', '1') != '0'
 
 
 @dataclass
@@ -108,8 +113,16 @@ class _SparseConv(torch.autograd.Function):
             dw = torch.empty((n_off, ci, co), dtype=torch.float32, device=src.device)
             lib = _lib.load()
             idx = geom.index
-            check(lib.tl_conv_wgrad(ptr(src), src.stride(0), ci, n_off, ptr(idx), 0 if idx is None else idx.stride(0),
-                                    ptr(geom.mask), ptr(d_out), geom.n_out, co, ptr(dw), int(mode != _lib.MODE_FP32), stream_ptr()))
+            istride = 0 if idx is None else idx.stride(0)
+            if mode != _lib.MODE_FP32 and USE_WGRAD_TC and lib.tl_conv_wgrad_tc_eligible(ci, co):
+                # tcgen05 weight gradient (csrc/tl_wgrad_tc.cu): TF32 operands straight from the fp32 tensors
+                wsb = lib.tl_conv_wgrad_tc_workspace_bytes(geom.n_out, ci, n_off, co)
+                ws = torch.empty(max(int(wsb), 256), dtype=torch.uint8, device=src.device)
+                check(lib.tl_conv_wgrad_tc(ptr(src), src.stride(0), ci, n_off, ptr(idx), istride, ptr(geom.mask), ptr(d_out),
+                                           geom.n_out, co, ptr(dw), ptr(ws), wsb, stream_ptr()))
+            else:
+                check(lib.tl_conv_wgrad(ptr(src), src.stride(0), ci, n_off, ptr(idx), istride, ptr(geom.mask), ptr(d_out),
+                                        geom.n_out, co, ptr(dw), int(mode != _lib.MODE_FP32), stream_ptr()))
             d_w = dw.permute(2, 0, 1).reshape(weight.shape).to(weight.dtype)
         return d_src, d_w, None, None
 

@@ -38,7 +38,10 @@ using namespace tl::tc;
 constexpr int MAX_G = 3;
 constexpr int MAX_NB = 64;                 // weight ring slots
 constexpr int NOFF = 27;
-constexpr int LIDX_BYTES = NOFF * BM * 2;  // the tile's rulebook as 16-bit halo indices
+constexpr int LIDX_ROWS = NOFF + 1;        // 27 rulebook rows + the lane -> tile row permutation
+constexpr int LIDX_BYTES = LIDX_ROWS * BM * 2;  // the tile's rulebook as 16-bit halo entries (position | swizzle key << 13), per LANE
+constexpr uint32_t POS_MASK = 0x1FFFu;
+constexpr int ROW_ID_BITS = 28;            // halo_rows entry = row id | class << 28 (-1 = unused position)
 constexpr int TMEM_COLS = 512;
 
 struct Launch {
@@ -326,8 +329,9 @@ __global__ void __launch_bounds__(32 * (5 * G + 1), 1) k_conv_halo(const tl_conv
                 for (int u = 0; u < 8; ++u) {
                     if (rid[u] < 0) continue;
                     const uint32_t hr = (uint32_t)(r0 + u * RPI + rsub) + 1u;
-                    const uint32_t sw = NSPLIT == 1 ? ((hr >> 1) & 3u) : (hr & 7u);
-                    cp_async16_cg(hbuf + hr * ROWB + ((p ^ sw) << 4), src + (size_t)rid[u] * rb + p * 16u, 16u);
+                    const uint32_t cls = (uint32_t)rid[u] >> ROW_ID_BITS;                  // the row's parity class = its swizzle key
+                    const uint32_t sw = NSPLIT == 1 ? (cls & 3u) : cls;                    // (f16: bit 2 of the class is the position's parity)
+                    cp_async16_cg(hbuf + hr * ROWB + ((p ^ sw) << 4), src + (size_t)(rid[u] & ((1 << ROW_ID_BITS) - 1)) * rb + p * 16u, 16u);
                 }
             }
             if (with_lidx) {
@@ -349,6 +353,7 @@ __global__ void __launch_bounds__(32 * (5 * G + 1), 1) k_conv_halo(const tl_conv
             const int next_tile = ((r + 1) * (int)gridDim.x + (int)blockIdx.x) * G + g;
             int s = 0;
             uint32_t kb = 0;
+            int prow[4] = {0, 0, 0, 0};
             const uint32_t lbuf = lbuf0 + lsel * LIDX_BYTES;
             for (uint32_t j = 0; j < (uint32_t)P.n_slices; ++j) {
                 const uint32_t hbuf = hbuf0 + hsel * hbytes;
@@ -364,18 +369,25 @@ __global__ void __launch_bounds__(32 * (5 * G + 1), 1) k_conv_halo(const tl_conv
                 };
                 cp_async_wait_all();
                 bar_sync(bar_id, 128);       // this slice (and the rulebook) has landed for all 4 warps; the previous slice is read out
+                if (j == 0) {                // tile rows of the 4 TMEM lanes this thread writes out (the rulebook buffer may be refilled before the epilogue)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) prow[i] = (int)ld_shared_u16(lbuf + 2u * (uint32_t)(NOFF * BM + qtr * 32 + rr + 8 * i));
+                }
                 if (dbl) prefetch();         // into the other buffer, while this slice is used
                 const uint32_t lrow = lbuf + 2u * (uint32_t)tid;
 #pragma unroll 1
                 for (uint32_t f = 0; f < NFILL; ++f) {
                     // the shared-memory reads do not depend on the fill's tensor-memory slot: issue the first ones before the wait
+                    // (measured, round 2: fetching the rulebook entries one fill ahead and the halo row ids two tiles ahead
+                    // into shared memory changes nothing -- 14.98 vs 14.97 ms of conv time per step -- although 20 % of the
+                    // stall samples sit on those loads: the groups hide each other's latencies)
                     uint32_t rowa[FILL], swz[FILL];
 #pragma unroll
                     for (uint32_t c = 0; c < FILL; ++c) {
                         const uint32_t k = min(f * FILL + c, (uint32_t)NOFF - 1u);
                         const uint32_t li = ld_shared_u16(lrow + k * (2u * BM));
-                        rowa[c] = li ? hbuf + li * ROWB : 0u;          // 0 = absent neighbour: zeros without touching shared memory
-                        swz[c] = NSPLIT == 1 ? ((li >> 1) & 3u) : (li & 7u);
+                        rowa[c] = li ? hbuf + (li & POS_MASK) * ROWB : 0u;          // 0 = absent neighbour: zeros without touching shared memory
+                        swz[c] = NSPLIT == 1 ? ((li >> 13) & 3u) : (li >> 13);
                     }
                     const uint32_t ta = a_col0 + a_slot * A_COLS;
                     if (NSPLIT == 1) {           // two chunks (8 LDS.128) in flight
@@ -427,13 +439,13 @@ __global__ void __launch_bounds__(32 * (5 * G + 1), 1) k_conv_halo(const tl_conv
 
             // ---- epilogue: this warp's 32 rows; lane (rr, q) holds positions 8q .. 8q+7 of every 32-channel block of rows
             //      rr, rr + 8 (half 0) and rr + 16, rr + 24 (half 1) of its quarter
-            const int64_t row0 = (int64_t)tile * BM + qtr * 32 + rr;
+            const int64_t trow0 = (int64_t)tile * BM;       // TMEM lane qtr * 32 + rr + 8 i holds tile row prow[i]
             const bool has_res = d.residual != nullptr;
             float4 res[4][2];
             auto fetch_residual = [&](int c0) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const int64_t grow = row0 + 8 * i;
+                    const int64_t grow = trow0 + prow[i];
                     res[i][0] = res[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (has_res && grow < d.n_out) {
                         const float4* p = reinterpret_cast<const float4*>(d.residual + grow * N + c0 + 8 * q);
@@ -466,7 +478,7 @@ __global__ void __launch_bounds__(32 * (5 * G + 1), 1) k_conv_halo(const tl_conv
                     if (d.out_raw) {
 #pragma unroll
                         for (int ab = 0; ab < 2; ++ab) {
-                            const int64_t grow = row0 + 16 * h + 8 * ab;
+                            const int64_t grow = trow0 + prow[2 * h + ab];
                             if (grow >= d.n_out) continue;
                             float4* p = reinterpret_cast<float4*>(d.out_raw + grow * N + c0 + 8 * q);
                             p[0] = make_float4(x[ab][0], x[ab][1], x[ab][2], x[ab][3]);
@@ -488,7 +500,7 @@ __global__ void __launch_bounds__(32 * (5 * G + 1), 1) k_conv_halo(const tl_conv
                         }
 #pragma unroll
                         for (int ab = 0; ab < 2; ++ab) {
-                            const int64_t grow = row0 + 16 * h + 8 * ab;
+                            const int64_t grow = trow0 + prow[2 * h + ab];
                             if (grow >= d.n_out) continue;
                             float a[8];
 #pragma unroll
@@ -536,23 +548,42 @@ static int launch(const tl_conv_desc& d, const Launch& P, int grid, size_t smem,
     return TL_OK;
 }
 
-// ---- tl_halo_build: per 128-row tile, the sorted list of distinct neighbour rows and the rulebook as indices into it ----
+// ---- tl_halo_build: per 128-row tile, the list of distinct neighbour rows and the rulebook as entries into it ----------
+// Bank-conflict-free by construction (profiles/r02_conv_history.md, "class swizzle"): a voxel's PARITY CLASS
+// cls = (x & 1) << 2 | (y & 1) << 1 | (z & 1) is the low 3 bits of its Morton key.  A halo row is stored with its 16 B pieces
+// XOR-swizzled by its class (the position's parity supplies bit 2 for 64 B rows), and the tile's rows are PERMUTED over the
+// 128 lanes so that the 8 lanes of a shared-memory phase hold 8 different classes wherever the tile's class histogram
+// allows (<= 16 rows per class).  The neighbours at one kernel offset of 8 voxels of different classes again have 8
+// different classes (a translation flips the same parity bits for all of them), so the 8 lanes of every LDS.128 phase of
+// the conv kernel hit 8 different bank groups for every one of the 27 offsets.
+//   halo_rows[tile][p - 1] = row id | cls << 28 at position p >= 1 (-1 = unused position; p is odd iff cls bit 2 is set)
+//   lidx[tile][k][lane]    = p | cls << 13 of the neighbour at offset k of the tile row held by `lane` (0 = absent)
+//   lidx[tile][27][lane]   = that tile row (lane -> row permutation)
 constexpr int HB_THREADS = 256;
 constexpr int HB_TABLE = 4096;       // open-addressing table, > the 3456 entries of a tile
 constexpr int HB_SORT = 2048;        // largest `cap`
 constexpr int HB_PER = (NOFF * BM + HB_THREADS - 1) / HB_THREADS;      // rulebook entries per thread (14)
 
-__global__ void __launch_bounds__(HB_THREADS) k_halo_build(const int32_t* __restrict__ nbr, int64_t n, int64_t stride, int cap,
-                                                            int32_t* __restrict__ halo_rows, int32_t* __restrict__ halo_cnt,
-                                                            uint16_t* __restrict__ lidx, int32_t* __restrict__ max_cnt) {
+__global__ void __launch_bounds__(HB_THREADS) k_halo_build(const int32_t* __restrict__ nbr, const uint64_t* __restrict__ keys, int64_t n,
+                                                            int64_t stride, int cap, int32_t* __restrict__ halo_rows,
+                                                            int32_t* __restrict__ halo_cnt, uint16_t* __restrict__ lidx,
+                                                            int32_t* __restrict__ max_cnt) {
     __shared__ int table[HB_TABLE];
-    __shared__ unsigned short rank[HB_TABLE];      // table slot -> 1-based position of its row in the sorted list
+    __shared__ unsigned short rank[HB_TABLE];      // table slot -> position | class << 13 of its row
     __shared__ int list[HB_SORT];
+    __shared__ unsigned short pos_list[HB_SORT];   // sorted-list index -> position | class << 13
     __shared__ int warp_tot[HB_THREADS / 32];
-    __shared__ int total_s;
+    __shared__ int total_s, used_s;
+    __shared__ unsigned char cls_row[BM], lane_of[BM], taken[BM], hole_list[BM], cls_list[HB_SORT];
+    __shared__ unsigned char cnt_wc[BM / 32][8], left_w[BM / 32], hole_w[BM / 32];
     const int tile = blockIdx.x, t = threadIdx.x;
     const int64_t row0 = (int64_t)tile * BM;
     for (int i = t; i < HB_TABLE; i += HB_THREADS) table[i] = -1;
+    if (t < BM) {
+        cls_row[t] = row0 + t < n ? (unsigned char)(__ldg(keys + row0 + t) & 7u) : (unsigned char)(t & 7);
+        taken[t] = 0;
+        if (t < (BM / 32) * 8) (&cnt_wc[0][0])[t] = 0;
+    }
     // this thread's entries e = t + 256 i (offset e / 128, row e % 128): loaded once, kept in registers with their table slot
     int val[HB_PER];
     unsigned short slot[HB_PER];
@@ -563,6 +594,23 @@ __global__ void __launch_bounds__(HB_THREADS) k_halo_build(const int32_t* __rest
         val[i] = (e < NOFF * BM && row0 + r < n) ? __ldg(nbr + (size_t)k * stride + row0 + r) : -1;
     }
     __syncthreads();
+    // ---- lane permutation: the j-th row of class c takes lane 8 j + c (phase j); rows beyond 16 of a class fill the holes
+    const uint32_t lt = (1u << (t & 31)) - 1u;
+    const int my_cls = t < BM ? cls_row[t] : 0;
+    int rk = 0;
+    if (t < BM) {       // warps 0-3, whole warps
+        const uint32_t same = __match_any_sync(0xffffffffu, my_cls);
+        rk = __popc(same & lt);
+        if (rk == 0) cnt_wc[t >> 5][my_cls] = (unsigned char)__popc(same);
+    }
+    __syncthreads();
+    if (t < BM) {
+        for (int w = 0; w < (t >> 5); ++w) rk += cnt_wc[w][my_cls];
+        if (rk < 16) {
+            lane_of[t] = (unsigned char)(8 * rk + my_cls);
+            taken[8 * rk + my_cls] = 1;
+        }
+    }
 #pragma unroll
     for (int i = 0; i < HB_PER; ++i) {
         const int v = val[i];
@@ -576,6 +624,21 @@ __global__ void __launch_bounds__(HB_THREADS) k_halo_build(const int32_t* __rest
         slot[i] = (unsigned short)h;
     }
     __syncthreads();
+    // the i-th left-over row (row order) takes the i-th free lane (lane order)
+    const bool is_left = t < BM && rk >= 16, is_hole = t < BM && !taken[t];
+    uint32_t bl = 0, bh = 0;
+    if (t < BM) {
+        bl = __ballot_sync(0xffffffffu, is_left), bh = __ballot_sync(0xffffffffu, is_hole);
+        if ((t & 31) == 0) left_w[t >> 5] = (unsigned char)__popc(bl), hole_w[t >> 5] = (unsigned char)__popc(bh);
+    }
+    __syncthreads();
+    int pl = __popc(bl & lt), ph = __popc(bh & lt);
+    if (t < BM) {
+        for (int w = 0; w < (t >> 5); ++w) pl += left_w[w], ph += hole_w[w];
+        if (is_hole) hole_list[ph] = (unsigned char)t;
+    }
+    __syncthreads();
+    if (is_left) lane_of[t] = hole_list[pl];
     // compact the occupied slots: each thread owns HB_TABLE / HB_THREADS consecutive slots
     constexpr int PER = HB_TABLE / HB_THREADS;
     int mine = 0;
@@ -599,11 +662,10 @@ __global__ void __launch_bounds__(HB_THREADS) k_halo_build(const int32_t* __rest
     }
     __syncthreads();
     const int total = total_s;
-    if (t == 0) {
-        halo_cnt[tile] = total <= cap ? total : 0;
-        atomicMax(max_cnt, total);
+    if (total > cap) {                           // the caller sees max_cnt > cap and does not use the halo kernel
+        if (t == 0) halo_cnt[tile] = 0, atomicMax(max_cnt, total);
+        return;
     }
-    if (total > cap) return;                     // the caller sees max_cnt > cap and does not use the halo kernel
     int at = warp_tot[t >> 5] + incl - mine;
 #pragma unroll
     for (int i = 0; i < PER; ++i) {
@@ -627,19 +689,48 @@ __global__ void __launch_bounds__(HB_THREADS) k_halo_build(const int32_t* __rest
             __syncthreads();
         }
     }
-    for (int i = t; i < total; i += HB_THREADS) {
-        const int v = list[i];
-        halo_rows[(size_t)tile * cap + i] = v;
-        uint32_t h = ((uint32_t)v * 2654435761u) >> 20;
-        while (table[h] != v) h = (h + 1) & (HB_TABLE - 1);
-        rank[h] = (unsigned short)(i + 1);        // 0 = the zero row
+    // ---- positions: rows whose class has bit 2 clear take the even positions 2, 4, ..., the others the odd ones 1, 3, ...
+    for (int i = t; i < total; i += HB_THREADS) cls_list[i] = (unsigned char)(__ldg(keys + list[i]) & 7u);
+    __syncthreads();
+    if (t < 32) {
+        int n0 = 0, n1 = 0;
+        for (int base = 0; base < total; base += 32) {
+            const int i = base + t;
+            const uint32_t cv = i < total ? (uint32_t)cls_list[i] : 0u;
+            const bool odd = i < total && (cv & 4u);
+            const bool even = i < total && !(cv & 4u);
+            const uint32_t bo = __ballot_sync(0xffffffffu, odd), be = __ballot_sync(0xffffffffu, even);
+            if (odd) pos_list[i] = (unsigned short)((1 + 2 * (n1 + __popc(bo & lt))) | (cv << 13));
+            if (even) pos_list[i] = (unsigned short)((2 + 2 * (n0 + __popc(be & lt))) | (cv << 13));
+            n1 += __popc(bo), n0 += __popc(be);
+        }
+        if (t == 0) used_s = max(2 * n0, 2 * n1 - 1);
     }
     __syncthreads();
+    const int used = used_s;
+    if (t == 0) {
+        halo_cnt[tile] = used <= cap ? used : 0;
+        atomicMax(max_cnt, used);
+    }
+    if (used > cap) return;
+    for (int i = t; i < used; i += HB_THREADS) halo_rows[(size_t)tile * cap + i] = -1;
+    __syncthreads();
+    for (int i = t; i < total; i += HB_THREADS) {
+        const int v = list[i];
+        const uint32_t pc = pos_list[i];
+        halo_rows[(size_t)tile * cap + (pc & POS_MASK) - 1] = v | (int)((pc >> 13) << ROW_ID_BITS);
+        uint32_t h = ((uint32_t)v * 2654435761u) >> 20;
+        while (table[h] != v) h = (h + 1) & (HB_TABLE - 1);
+        rank[h] = (unsigned short)pc;
+    }
+    __syncthreads();
+    uint16_t* out = lidx + (size_t)tile * (LIDX_ROWS * BM);
 #pragma unroll
     for (int i = 0; i < HB_PER; ++i) {
         const int e = t + HB_THREADS * i;
-        if (e < NOFF * BM) lidx[(size_t)tile * (NOFF * BM) + e] = val[i] >= 0 ? rank[slot[i]] : (unsigned short)0;
+        if (e < NOFF * BM) out[(e / BM) * BM + lane_of[e % BM]] = val[i] >= 0 ? rank[slot[i]] : (unsigned short)0;
     }
+    if (t < BM) out[NOFF * BM + lane_of[t]] = (unsigned short)t;
 }
 
 }  // namespace halo
@@ -735,15 +826,15 @@ int conv_fwd_halo(const tl_conv_desc& d, cudaStream_t stream, int nsplit) {
 
 }  // namespace tl
 
-extern "C" int tl_halo_build(const int32_t* nbr, int64_t n, int64_t nbr_stride, int32_t cap, int32_t* halo_rows, int32_t* halo_cnt,
-                             uint16_t* halo_lidx, int32_t* max_cnt, void* stream) {
+extern "C" int tl_halo_build(const int32_t* nbr, const uint64_t* keys, int64_t n, int64_t nbr_stride, int32_t cap, int32_t* halo_rows,
+                             int32_t* halo_cnt, uint16_t* halo_lidx, int32_t* max_cnt, void* stream) {
     if (n <= 0) return TL_OK;
-    if (!nbr || !halo_rows || !halo_cnt || !halo_lidx || !max_cnt || cap <= 0 || cap > tl::halo::HB_SORT) {
+    if (!nbr || !keys || n >= (1ll << tl::halo::ROW_ID_BITS) || !halo_rows || !halo_cnt || !halo_lidx || !max_cnt || cap <= 0 || cap > tl::halo::HB_SORT) {
         tl::set_error("tl_halo_build: bad argument");
         return TL_ERR_ARG;
     }
     const int tiles = (int)((n + tl::tc::BM - 1) / tl::tc::BM);
-    tl::halo::k_halo_build<<<tiles, tl::halo::HB_THREADS, 0, (cudaStream_t)stream>>>(nbr, n, nbr_stride, cap, halo_rows, halo_cnt, halo_lidx, max_cnt);
+    tl::halo::k_halo_build<<<tiles, tl::halo::HB_THREADS, 0, (cudaStream_t)stream>>>(nbr, keys, n, nbr_stride, cap, halo_rows, halo_cnt, halo_lidx, max_cnt);
     TL_LAUNCH_CHECK();
     return TL_OK;
 }

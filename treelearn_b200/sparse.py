@@ -188,7 +188,8 @@ def build_subm_rulebook(lv):
 
 
 class Halo:
-    """Per 128-row tile of a level: the distinct neighbour rows and the 3^3 rulebook as 16-bit indices into that list
+    """Per 128-row tile of a level: the distinct neighbour rows (`rows`: row id | parity class << 28 per list position), the
+    3^3 rulebook as 16-bit entries into that list per lane and the lane -> tile row permutation (`lidx` [tiles, 28, 128])
     (tl_halo_build, csrc/tl_conv_halo.cu).  Hangs off the level's `nbr` tensor so that sparse.conv finds it from the
     segments' index tensors.  `umax` (largest list of the level) costs one host read of an int32."""
 
@@ -212,9 +213,9 @@ def build_halo(lv, cap=None):
     cap = cap or HALO_CAP
     tiles = pad_rows(lv.n) // TILE_ROWS
     h = Halo(torch.empty((tiles, cap), dtype=torch.int32, device=dev), torch.empty(tiles, dtype=torch.int32, device=dev),
-             torch.empty((tiles, 27, TILE_ROWS), dtype=torch.int16, device=dev), torch.zeros(1, dtype=torch.int32, device=dev), cap)
-    check(lib.tl_halo_build(ptr(lv.nbr), lv.n, lv.nbr.stride(0), cap, ptr(h.rows), ptr(h.cnt), ptr(h.lidx), ptr(h.max_cnt),
-                            stream_ptr()))
+             torch.empty((tiles, 28, TILE_ROWS), dtype=torch.int16, device=dev), torch.zeros(1, dtype=torch.int32, device=dev), cap)
+    check(lib.tl_halo_build(ptr(lv.nbr), ptr(lv.keys), lv.n, lv.nbr.stride(0), cap, ptr(h.rows), ptr(h.cnt), ptr(h.lidx),
+                            ptr(h.max_cnt), stream_ptr()))
     lv.nbr.halo = h
     return h
 
