@@ -141,6 +141,113 @@ __global__ void __launch_bounds__(256) k_bn_relu_bwd_apply(const float* __restri
         }
 }
 
+// ---- float4 forms (c % 4 == 0, c <= 512; rows are 16 B aligned): the scalar kernels above drew 0.46-0.75 TB/s of HBM
+// (profiles/r02_ncu_launches_summary_train.txt: one 4 B load per lane and iteration, an int64 modulo per element)
+// One thread keeps ONE float4 column (t % c4) and strides over the rows: S = the largest multiple of c4 <= 256 threads
+// are active, S / c4 rows per pass; fp32 partial sums per thread, fp64 across threads and blocks.
+template <bool BWD>
+__global__ void __launch_bounds__(256) k_bn_reduce_v4(const float* __restrict__ x, const float* __restrict__ d_act, int64_t n, int c,
+                                                      int rows_per_block, const float* __restrict__ scale,
+                                                      const float* __restrict__ shift, const float* __restrict__ mean,
+                                                      const float* __restrict__ invstd, double* __restrict__ acc) {
+    __shared__ float4 red[2][256];
+    const int c4 = c >> 2, t = threadIdx.x;
+    const int rpp = 256 / c4, S = rpp * c4;
+    const int col4 = t % c4, roff = t / c4;
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+    const int64_t r1 = min(r0 + (int64_t)rows_per_block, n);
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+    if (t < S) {
+        const float4* x4 = reinterpret_cast<const float4*>(x) + col4;
+        const float4* d4 = reinterpret_cast<const float4*>(d_act) + col4;
+        float4 sc = s, sh = s, m = s, is = s;
+        if (BWD) {
+            sc = __ldg(reinterpret_cast<const float4*>(scale) + col4), sh = __ldg(reinterpret_cast<const float4*>(shift) + col4);
+            m = __ldg(reinterpret_cast<const float4*>(mean) + col4), is = __ldg(reinterpret_cast<const float4*>(invstd) + col4);
+        }
+#pragma unroll 4
+        for (int64_t r = r0 + roff; r < r1; r += rpp) {
+            const float4 v = __ldg(x4 + r * c4);
+            if (BWD) {
+                const float4 g = __ldg(d4 + r * c4);
+                const float dx_ = fmaf(v.x, sc.x, sh.x) > 0.f ? g.x : 0.f, dy_ = fmaf(v.y, sc.y, sh.y) > 0.f ? g.y : 0.f;
+                const float dz_ = fmaf(v.z, sc.z, sh.z) > 0.f ? g.z : 0.f, dw_ = fmaf(v.w, sc.w, sh.w) > 0.f ? g.w : 0.f;
+                s.x += dx_, s.y += dy_, s.z += dz_, s.w += dw_;
+                q.x = fmaf(dx_, (v.x - m.x) * is.x, q.x), q.y = fmaf(dy_, (v.y - m.y) * is.y, q.y);
+                q.z = fmaf(dz_, (v.z - m.z) * is.z, q.z), q.w = fmaf(dw_, (v.w - m.w) * is.w, q.w);
+            } else {
+                s.x += v.x, s.y += v.y, s.z += v.z, s.w += v.w;
+                q.x = fmaf(v.x, v.x, q.x), q.y = fmaf(v.y, v.y, q.y), q.z = fmaf(v.z, v.z, q.z), q.w = fmaf(v.w, v.w, q.w);
+            }
+        }
+    }
+    red[0][t] = s, red[1][t] = q;
+    __syncthreads();
+    if (t < c4) {
+        double ds[4] = {0, 0, 0, 0}, dq[4] = {0, 0, 0, 0};
+        for (int j = 0; j < rpp; ++j) {
+            const float4 a = red[0][j * c4 + t], b = red[1][j * c4 + t];
+            ds[0] += (double)a.x, ds[1] += (double)a.y, ds[2] += (double)a.z, ds[3] += (double)a.w;
+            dq[0] += (double)b.x, dq[1] += (double)b.y, dq[2] += (double)b.z, dq[3] += (double)b.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            atomicAdd(acc + 4 * t + i, ds[i]);
+            atomicAdd(acc + c + 4 * t + i, dq[i]);
+        }
+    }
+}
+
+// elementwise passes over [n, c] as float4 columns: MODE 0 out = relu(scale x + shift); MODE 1 the BN+ReLU input gradient
+template <int MODE>
+__global__ void __launch_bounds__(256) k_bn_elem_v4(const float* __restrict__ x, const float* __restrict__ d_act, int64_t n, int c,
+                                                    const float* __restrict__ scale, const float* __restrict__ shift,
+                                                    const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                    const double* __restrict__ acc, int batch_stats, float* __restrict__ out,
+                                                    float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    const int c4 = c >> 2, t = threadIdx.x;
+    const int rpp = 256 / c4, S = rpp * c4;
+    if (MODE == 1 && blockIdx.x == 0)
+        for (int j = t; j < c; j += 256) {
+            if (dbeta) dbeta[j] = (float)acc[j];
+            if (dgamma) dgamma[j] = (float)acc[c + j];
+        }
+    if (t >= S) return;
+    const int col4 = t % c4, roff = t / c4;
+    const float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + col4), sh = __ldg(reinterpret_cast<const float4*>(shift) + col4);
+    float4 m = sc, is = sc, a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+    if (MODE == 1 && batch_stats) {
+        m = __ldg(reinterpret_cast<const float4*>(mean) + col4), is = __ldg(reinterpret_cast<const float4*>(invstd) + col4);
+        const double inv_n = 1.0 / (double)n;
+        a0 = make_float4((float)(acc[4 * col4] * inv_n), (float)(acc[4 * col4 + 1] * inv_n), (float)(acc[4 * col4 + 2] * inv_n),
+                         (float)(acc[4 * col4 + 3] * inv_n));
+        a1 = make_float4((float)(acc[c + 4 * col4] * inv_n), (float)(acc[c + 4 * col4 + 1] * inv_n), (float)(acc[c + 4 * col4 + 2] * inv_n),
+                         (float)(acc[c + 4 * col4 + 3] * inv_n));
+    }
+    const float4* x4 = reinterpret_cast<const float4*>(x) + col4;
+    const float4* d4 = reinterpret_cast<const float4*>(d_act) + col4;
+    float4* o4 = reinterpret_cast<float4*>(out) + col4;
+#pragma unroll 4
+    for (int64_t r = (int64_t)blockIdx.x * rpp + roff; r < n; r += (int64_t)gridDim.x * rpp) {
+        const float4 v = __ldg(x4 + r * c4);
+        float4 o;
+        if (MODE == 0) {
+            o = make_float4(fmaxf(fmaf(v.x, sc.x, sh.x), 0.f), fmaxf(fmaf(v.y, sc.y, sh.y), 0.f), fmaxf(fmaf(v.z, sc.z, sh.z), 0.f),
+                            fmaxf(fmaf(v.w, sc.w, sh.w), 0.f));
+        } else {
+            const float4 g = __ldg(d4 + r * c4);
+            float4 dy = make_float4(fmaf(v.x, sc.x, sh.x) > 0.f ? g.x : 0.f, fmaf(v.y, sc.y, sh.y) > 0.f ? g.y : 0.f,
+                                    fmaf(v.z, sc.z, sh.z) > 0.f ? g.z : 0.f, fmaf(v.w, sc.w, sh.w) > 0.f ? g.w : 0.f);
+            if (batch_stats) {
+                dy.x = dy.x - a0.x - (v.x - m.x) * is.x * a1.x, dy.y = dy.y - a0.y - (v.y - m.y) * is.y * a1.y;
+                dy.z = dy.z - a0.z - (v.z - m.z) * is.z * a1.z, dy.w = dy.w - a0.w - (v.w - m.w) * is.w * a1.w;
+            }
+            o = make_float4(sc.x * dy.x, sc.y * dy.y, sc.z * dy.z, sc.w * dy.w);
+        }
+        o4[r * c4] = o;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // weight gradient: dw[k][ci][co] += sum_r src[index[k][r], ci] * d_out[r, co]
 // One CTA (64 threads, 4x4 register tile each) owns a 32x32 (ci, co) tile of one offset k over a slab of rows;
@@ -403,7 +510,11 @@ int tl_bn_stats(const float* x, int64_t n, int32_t c, double* acc, void* stream_
     TL_REQUIRE(x && acc && n > 0 && c > 0 && c <= 32 * train::kMaxCB, "tl_bn_stats: n=%lld c=%d", (long long)n, c);
     TL_CUDA_CHECK(cudaMemsetAsync(acc, 0, sizeof(double) * 2 * c, stream));
     const int rpb = train::rows_per_block_for(n, 148 * 8);
-    train::k_bn_stats<<<(unsigned)((n + rpb - 1) / rpb), 256, 0, stream>>>(x, n, c, rpb, acc);
+    if (c % 4 == 0)
+        train::k_bn_reduce_v4<false><<<(unsigned)((n + rpb - 1) / rpb), 256, 0, stream>>>(x, nullptr, n, c, rpb, nullptr, nullptr, nullptr,
+                                                                                        nullptr, acc);
+    else
+        train::k_bn_stats<<<(unsigned)((n + rpb - 1) / rpb), 256, 0, stream>>>(x, n, c, rpb, acc);
     TL_LAUNCH_CHECK();
     return TL_OK;
 }
@@ -426,7 +537,13 @@ int tl_bn_relu_apply(const float* x, int64_t n, int32_t c, const float* scale, c
     TL_REQUIRE(x && scale && shift && out && c > 0, "tl_bn_relu_apply: bad arguments");
     const int64_t total = n * c;
     const unsigned grid = (unsigned)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
-    train::k_bn_relu_apply<<<grid, 256, 0, stream>>>(x, total, c, scale, shift, out);
+    if (c % 4 == 0 && c <= 512) {
+        const int64_t passes = (n + (256 / (c / 4)) - 1) / (256 / (c / 4));
+        train::k_bn_elem_v4<0><<<(unsigned)(passes > 148 * 16 ? 148 * 16 : passes), 256, 0, stream>>>(
+            x, nullptr, n, c, scale, shift, nullptr, nullptr, nullptr, 0, out, nullptr, nullptr);
+    } else {
+        train::k_bn_relu_apply<<<grid, 256, 0, stream>>>(x, total, c, scale, shift, out);
+    }
     TL_LAUNCH_CHECK();
     return TL_OK;
 }
@@ -440,13 +557,23 @@ int tl_bn_relu_bwd(const float* x, const float* d_act, int64_t n, int32_t c, con
                "tl_bn_relu_bwd: bad arguments");
     TL_CUDA_CHECK(cudaMemsetAsync(acc, 0, sizeof(double) * 2 * c, stream));
     const int rpb = train::rows_per_block_for(n, 148 * 8);
-    train::k_bn_relu_bwd_reduce<<<(unsigned)((n + rpb - 1) / rpb), 256, 0, stream>>>(x, d_act, n, c, rpb, scale, shift,
-                                                                                   mean, invstd, acc);
+    if (c % 4 == 0)
+        train::k_bn_reduce_v4<true><<<(unsigned)((n + rpb - 1) / rpb), 256, 0, stream>>>(x, d_act, n, c, rpb, scale, shift, mean,
+                                                                                       invstd, acc);
+    else
+        train::k_bn_relu_bwd_reduce<<<(unsigned)((n + rpb - 1) / rpb), 256, 0, stream>>>(x, d_act, n, c, rpb, scale, shift,
+                                                                                       mean, invstd, acc);
     TL_LAUNCH_CHECK();
     const int64_t total = n * c;
     const unsigned grid = (unsigned)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
-    train::k_bn_relu_bwd_apply<<<grid, 256, 0, stream>>>(x, d_act, n, c, scale, shift, mean, invstd, acc, batch_stats, dx,
-                                                         dgamma, dbeta);
+    if (c % 4 == 0) {
+        const int64_t passes = (n + (256 / (c / 4)) - 1) / (256 / (c / 4));
+        train::k_bn_elem_v4<1><<<(unsigned)(passes > 148 * 16 ? 148 * 16 : passes), 256, 0, stream>>>(
+            x, d_act, n, c, scale, shift, mean, invstd, acc, batch_stats, dx, dgamma, dbeta);
+    } else {
+        train::k_bn_relu_bwd_apply<<<grid, 256, 0, stream>>>(x, d_act, n, c, scale, shift, mean, invstd, acc, batch_stats, dx,
+                                                             dgamma, dbeta);
+    }
     TL_LAUNCH_CHECK();
     return TL_OK;
 }
