@@ -57,6 +57,32 @@ def conv_traffic(workload, mode):
     return None, 'no capture for this workload/mode'
 
 
+def secondary_kernels(peak):
+    """Achieved DRAM GB/s of the non-conv kernels of the step (rulebook, scatter, clustering ...: the `north_star` evidence
+    list) from the committed ncu launch list profiles/r02_ncu_launches_summary_step_f16x2.txt (tools/summarise_launches.py
+    over `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum` of tools/profile_step.py, 3 steps).
+    ncu replays every launch cold-cache and serialised, so these are per-kernel DRAM rates, not shares of the live step."""
+    path = os.path.join(ROOT, 'profiles', 'r02_ncu_launches_summary_step_f16x2.txt')
+    if not os.path.exists(path):
+        return None
+    want = ('k_subm_probe', 'k_hash_build', 'k_halo_build', 'k_level_emit', 'k_emit_voxels', 'k_heads', 'k_cc_link',
+            'k_knn_vote', 'k_conv_in4', 'DeviceRadixSortOnesweep')
+    out = []
+    for line in open(path):
+        f = line.split()
+        if line.startswith('#') or len(f) < 8:
+            continue
+        name = ' '.join(f[7:])
+        hit = [w for w in want if w in name]
+        if not hit or any(o['kernel'] == hit[0] for o in out):
+            continue
+        us, n, rd, wr, gbs = float(f[1]), int(f[2]), float(f[3]), float(f[4]), float(f[5])
+        out.append({'kernel': hit[0], 'launches_per_step': round(n / 3, 1), 'us_per_step': round(us / 3, 1),
+                    'dram_MB_per_step': round((rd + wr) / 3, 1), 'achieved_GBs': gbs, 'frac': round(gbs / peak, 4)})
+    return {'source': 'profiles/r02_ncu_launches_summary_step_f16x2.txt (ncu, cold-cache, serialised; 3 steps)', 'bound': 'hbm',
+            'kernels': out}
+
+
 def peaks():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
@@ -177,7 +203,7 @@ def train_record(args, world, rank, dev, dist):
     from treelearn_b200 import TreeLearn, synth, sparse
     from treelearn_b200 import dist as tdist
 
-    def run(n_tiles, seed0, steps=4, warmup=2):
+    def run(n_tiles, seed0, steps=8, warmup=6):   # GradScaler skips its first ~4 steps (scale 65536 -> 4096); AdamW state is created by the first real one
         tiles = [synth.synth_forest(edge=20.0, n_trees=20, seed=seed0 + s) for s in range(n_tiles)]
         batch = synth.make_batch(tiles)
         batch = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in batch.items()}
@@ -256,8 +282,10 @@ DTYPE_TEXT = {
 CONV_KERNEL = {
     'fp32': 'k_conv_simt (segmented gather-GEMM sparse conv, fp32 FMA)',
     'tf32': 'k_conv_tc (tcgen05 tf32 gather-GEMM sparse conv)',
-    'f16': 'k_conv_grp<1> (tcgen05 f16 gather-GEMM sparse conv, warp-group pipelines)',
-    'f16x2': 'k_conv_grp<2> (tcgen05 f16 hi/lo gather-GEMM sparse conv, warp-group pipelines)',
+    'f16': 'k_conv_halo<1> + k_conv_grp<1> (tcgen05 f16 sparse conv: halo-cached TS-form kernel for the 3^3 submanifold layers, '
+           'gather kernel for the strided / inverse layers); all conv launches of the step',
+    'f16x2': 'k_conv_halo<2> + k_conv_grp<2> (tcgen05 f16 hi/lo sparse conv: halo-cached TS-form kernel for the 3^3 submanifold '
+             'layers, gather kernel for the strided / inverse layers); all conv launches of the step',
 }
 
 
@@ -420,6 +448,9 @@ def run_b200(args):
                 'kernel_share_of_step': round(conv_ms / args.steps / ms_res, 3),
                 'alg_bytes_per_step': int(conv_bytes / args.steps),
                 'dense_tflops': round(conv_flops / (conv_ms * 1e-3) / 1e12, 2) if conv_ms > 0 else 0.0}
+    sec = secondary_kernels(peak)
+    if sec is not None:
+        roofline['secondary'] = sec
 
     # the single-term mode beside the headline (same weights, same tile, same trained-like correction)
     fast = None

@@ -1,0 +1,5 @@
+mkdir -p gpurun_out/r2h; O=gpurun_out/r2h
+timeout 1200 python -m pytest tests -m gpu -x -q > $O/pytest_gpu.log 2>&1; tail -4 $O/pytest_gpu.log
+timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:k_conv --csv --log-file $O/conv_traffic_f16x2.csv python tools/profile_layers.py cfg2_2M f16x2 > $O/ncu_traffic.log 2>&1; tail -2 $O/ncu_traffic.log | cut -c1-150
+timeout 600 python bench.py > $O/bench_n1.json 2> $O/bench_n1.err; tail -3 $O/bench_n1.err; python -c "
+import json;d=json.loads(open('$O/bench_n1.json').read().strip().splitlines()[-1]);print(d['value'],d['ms_per_step'],d['fwd_only'],d['e2e']['value'],d['roofline']['frac'],d['roofline']['kernel_ms_per_step'],json.dumps(d['train']['cfg3_4tile_batch']))"

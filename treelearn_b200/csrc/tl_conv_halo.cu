@@ -53,6 +53,10 @@ struct Launch {
     uint32_t b_bytes;
     int group_cols;      // TMEM columns per group: accumulator + 2 fills
     int nbuf;            // halo (and rulebook) buffers per group: 2 = the next slice is fetched while this one is used
+    // split-K for levels with fewer tiles than SMs (G == 1, rounds == 1, weight ring): CTA b owns tile b / splits and the K-slices
+    // [(b % splits) * slices_per_split, ...); accumulators are added into splitk_ws, k_splitk_epilogue_p applies the epilogue
+    int splits, slices_per_split;
+    float* splitk_ws;
 };
 
 struct Layout {
@@ -192,6 +196,13 @@ __global__ void __launch_bounds__(32 * (5 * G + 1), 1) k_conv_halo(const tl_conv
     uint32_t kb_cnt[TL_MAX_SEG];
 #pragma unroll
     for (int s = 0; s < TL_MAX_SEG; ++s) kb_cnt[s] = s < d.n_seg ? (uint32_t)d.seg[s].c_in / 32u : 0u;
+    // K-slice range of this CTA and the (segment, k-block, resident slab base) of its first slice
+    const bool SK = P.splits > 1;
+    const uint32_t j_begin = SK ? (uint32_t)((int)blockIdx.x % P.splits) * (uint32_t)P.slices_per_split : 0u;
+    const uint32_t j_end = SK ? min(j_begin + (uint32_t)P.slices_per_split, (uint32_t)P.n_slices) : (uint32_t)P.n_slices;
+    uint32_t s_begin = 0, kb_begin = 0, seg_base_begin = 0;
+    for (uint32_t jj = 0; jj < j_begin; ++jj)
+        if (++kb_begin == kb_cnt[s_begin]) seg_base_begin += (uint32_t)NOFF * kb_cnt[s_begin], kb_begin = 0, ++s_begin;
 
     if (warp == kAuxWarp) {
         if (RESIDENT) {
@@ -211,8 +222,8 @@ __global__ void __launch_bounds__(32 * (5 * G + 1), 1) k_conv_halo(const tl_conv
             __syncwarp();
         } else {
             // one weight stream for the whole CTA in the order the groups consume it: slice j (segment, k-block), offset k
-            const uint32_t total = (uint32_t)P.rounds * chunks_total;
-            uint32_t slot = 0, phase = 0, j = 0, k = 0, s = 0, kb = 0;
+            const uint32_t total = (uint32_t)P.rounds * (j_end - j_begin) * NOFF;
+            uint32_t slot = 0, phase = 0, j = j_begin, k = 0, s = s_begin, kb = kb_begin;
             for (uint32_t p = 0; p < total; ++p) {
                 mbar_wait(L.b_empty(slot), phase ^ 1u);
                 if (elect_one()) {
@@ -240,10 +251,10 @@ __global__ void __launch_bounds__(32 * (5 * G + 1), 1) k_conv_halo(const tl_conv
         if (RESIDENT) mbar_wait(L.wres(), 0u);
         uint32_t a_slot = 0, a_phase = 0, b_slot = 0, b_phase = 0;
         for (int r = 0; r < P.rounds; ++r) {
-            const int tile = (r * (int)gridDim.x + (int)blockIdx.x) * G + g;
+            const int tile = SK ? (int)blockIdx.x / P.splits : (r * (int)gridDim.x + (int)blockIdx.x) * G + g;
             const bool valid = tile < P.num_tiles;
-            uint32_t seg_base = 0, s = 0, kb = 0;                // resident slab numbering
-            for (uint32_t j = 0; j < (uint32_t)P.n_slices; ++j) {
+            uint32_t seg_base = seg_base_begin, s = s_begin, kb = kb_begin;                // resident slab numbering
+            for (uint32_t j = j_begin; j < j_end; ++j) {
                 for (uint32_t f = 0; f < NFILL; ++f) {
                     if (valid) {
                         mbar_wait(L.a_full(g, a_slot), a_phase);
@@ -266,7 +277,7 @@ __global__ void __launch_bounds__(32 * (5 * G + 1), 1) k_conv_halo(const tl_conv
                                 const uint64_t bd = bdesc0 + (uint64_t)boff;
 #pragma unroll
                                 for (uint32_t kk = 0; kk < 2; ++kk) {
-                                    umma_f16_ts(acc_col, a_col + 8 * kk, bd + 2 * kk, idesc, (j | k | kk) ? 1u : 0u);
+                                    umma_f16_ts(acc_col, a_col + 8 * kk, bd + 2 * kk, idesc, ((j - j_begin) | k | kk) ? 1u : 0u);
                                     if (NSPLIT == 2) {
                                         umma_f16_ts(acc_col, a_col + 8 * kk, bd + half16 + 2 * kk, idesc, 1u);      // hi x lo
                                         umma_f16_ts(acc_col, a_col + 16 + 8 * kk, bd + 2 * kk, idesc, 1u);          // lo x hi
@@ -344,21 +355,21 @@ __global__ void __launch_bounds__(32 * (5 * G + 1), 1) k_conv_halo(const tl_conv
         uint32_t a_slot = 0, a_phase = 0;
         uint32_t hsel = 0, lsel = 0;                     // buffer of the current slice / of the current tile's rulebook
         {
-            const int tile0 = (int)blockIdx.x * G + g;
-            if (tile0 < P.num_tiles) load_halo(tile0, 0, 0u, true, hbuf0, lbuf0);
+            const int tile0 = SK ? (int)blockIdx.x / P.splits : (int)blockIdx.x * G + g;
+            if (tile0 < P.num_tiles) load_halo(tile0, (int)s_begin, kb_begin, true, hbuf0, lbuf0);
         }
         for (int r = 0; r < P.rounds; ++r) {
-            const int tile = (r * (int)gridDim.x + (int)blockIdx.x) * G + g;
+            const int tile = SK ? (int)blockIdx.x / P.splits : (r * (int)gridDim.x + (int)blockIdx.x) * G + g;
             if (tile >= P.num_tiles) continue;           // (the group's MMA warp passes the weight stream on)
-            const int next_tile = ((r + 1) * (int)gridDim.x + (int)blockIdx.x) * G + g;
-            int s = 0;
-            uint32_t kb = 0;
+            const int next_tile = SK ? P.num_tiles : ((r + 1) * (int)gridDim.x + (int)blockIdx.x) * G + g;
+            int s = (int)s_begin;
+            uint32_t kb = kb_begin;
             int prow[4] = {0, 0, 0, 0};
             const uint32_t lbuf = lbuf0 + lsel * LIDX_BYTES;
-            for (uint32_t j = 0; j < (uint32_t)P.n_slices; ++j) {
+            for (uint32_t j = j_begin; j < j_end; ++j) {
                 const uint32_t hbuf = hbuf0 + hsel * hbytes;
                 // the slice after this one: the tile's next K-slice, or the next tile's first one (with its rulebook)
-                const bool last = j + 1 == (uint32_t)P.n_slices;
+                const bool last = j + 1 == j_end;
                 int ns = s;
                 uint32_t nkb = kb + 1;
                 if (nkb == kb_cnt[s]) nkb = 0, ++ns;
@@ -369,7 +380,7 @@ __global__ void __launch_bounds__(32 * (5 * G + 1), 1) k_conv_halo(const tl_conv
                 };
                 cp_async_wait_all();
                 bar_sync(bar_id, 128);       // this slice (and the rulebook) has landed for all 4 warps; the previous slice is read out
-                if (j == 0) {                // tile rows of the 4 TMEM lanes this thread writes out (the rulebook buffer may be refilled before the epilogue)
+                if (j == j_begin) {          // tile rows of the 4 TMEM lanes this thread writes out (the rulebook buffer may be refilled before the epilogue)
 #pragma unroll
                     for (int i = 0; i < 4; ++i) prow[i] = (int)ld_shared_u16(lbuf + 2u * (uint32_t)(NOFF * BM + qtr * 32 + rr + 8 * i));
                 }
@@ -440,7 +451,7 @@ __global__ void __launch_bounds__(32 * (5 * G + 1), 1) k_conv_halo(const tl_conv
             // ---- epilogue: this warp's 32 rows; lane (rr, q) holds positions 8q .. 8q+7 of every 32-channel block of rows
             //      rr, rr + 8 (half 0) and rr + 16, rr + 24 (half 1) of its quarter
             const int64_t trow0 = (int64_t)tile * BM;       // TMEM lane qtr * 32 + rr + 8 i holds tile row prow[i]
-            const bool has_res = d.residual != nullptr;
+            const bool has_res = d.residual != nullptr && !SK;      // split-K: the second pass adds the residual
             float4 res[4][2];
             auto fetch_residual = [&](int c0) {
 #pragma unroll
@@ -474,6 +485,17 @@ __global__ void __launch_bounds__(32 * (5 * G + 1), 1) k_conv_halo(const tl_conv
                         const float4 r0 = res[2 * h + ab][0], r1 = res[2 * h + ab][1];
                         x[ab][0] += r0.x, x[ab][1] += r0.y, x[ab][2] += r0.z, x[ab][3] += r0.w;
                         x[ab][4] += r1.x, x[ab][5] += r1.y, x[ab][6] += r1.z, x[ab][7] += r1.w;
+                    }
+                    if (SK) {                // partial sums of this CTA's K-slices -> fp32 scratch (P-layout positions, like out_raw)
+#pragma unroll
+                        for (int ab = 0; ab < 2; ++ab) {
+                            const int64_t grow = trow0 + prow[2 * h + ab];
+                            if (grow >= d.n_out) continue;
+                            float* p = P.splitk_ws + grow * N + c0 + 8 * q;
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(x[ab][0]), "f"(x[ab][1]), "f"(x[ab][2]), "f"(x[ab][3]) : "memory");
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p + 4), "f"(x[ab][4]), "f"(x[ab][5]), "f"(x[ab][6]), "f"(x[ab][7]) : "memory");
+                        }
+                        continue;
                     }
                     if (d.out_raw) {
 #pragma unroll
@@ -531,6 +553,22 @@ __global__ void __launch_bounds__(32 * (5 * G + 1), 1) k_conv_halo(const tl_conv
     __syncthreads();
     if (warp == kAuxWarp) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// split-K second pass over P-layout tensors: v = scratch (+ residual) -> raw / activated outputs; position m of a
+// 32-channel block holds logical channel p_chan(m) (scale / shift vectors are in logical order)
+template <int FMT>
+__global__ void __launch_bounds__(256) k_splitk_epilogue_p(const tl_conv_desc d, const float* __restrict__ ws) {
+    const int64_t total = (int64_t)d.n_out * d.c_out;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int col = (int)(e % d.c_out);
+        const int ch = (col & ~31) + p_chan(col & 31);
+        float v = ws[e];
+        if (d.residual) v += __ldg(d.residual + e);
+        if (d.out_raw) d.out_raw[e] = v;
+        if (d.out_act1) store_act1<FMT>(d.out_act1, e, d.c_out, fmaxf(fmaf(v, __ldg(d.scale1 + ch), __ldg(d.shift1 + ch)), 0.f));
+        if (d.out_act2) store_act1<FMT>(d.out_act2, e, d.c_out, fmaxf(fmaf(v, __ldg(d.scale2 + ch), __ldg(d.shift2 + ch)), 0.f));
     }
 }
 
@@ -780,9 +818,21 @@ int conv_fwd_halo(const tl_conv_desc& d, cudaStream_t stream, int nsplit) {
     if (G > halo::MAX_G) G = halo::MAX_G;
     if (env_int_halo("TL_HALO_GROUPS", 0) > 0 && env_int_halo("TL_HALO_GROUPS", 0) < G) G = env_int_halo("TL_HALO_GROUPS", 0);
     while (G > 1 && (G - 1) * sms >= P.num_tiles) --G;          // small levels: spread the tiles over the SMs first
+    // levels with fewer tiles than half the SMs (the two or three deepest): one tile is a serial chain of n_slices x 27 chunks
+    // of N-wide MMAs on ONE SM (measured 70-120 us per launch for a few thousand voxels) -> split the K-slices over CTAs
+    P.splits = 1, P.slices_per_split = P.n_slices;
+    if (d.splitk_ws && P.n_slices >= 2 && env_int_halo("TL_HALO_SPLITK", 1) != 0) {
+        int sp = sms / P.num_tiles;
+        if (sp > P.n_slices) sp = P.n_slices;
+        if (sp >= 2) {
+            P.slices_per_split = (P.n_slices + sp - 1) / sp;
+            P.splits = (P.n_slices + P.slices_per_split - 1) / P.slices_per_split;
+        }
+    }
+    if (P.splits > 1) G = 1;
     // per G: resident weights + two halo buffers, else resident + one, else a weight ring (>= 4 slabs) + two, else ring + one
     int resident = 0, nbuf = 1;
-    const bool allow_res = env_int_halo("TL_HALO_RESIDENT", 1) != 0, allow_dbl = env_int_halo("TL_HALO_DOUBLE", 1) != 0;
+    const bool allow_res = env_int_halo("TL_HALO_RESIDENT", 1) != 0 && P.splits == 1, allow_dbl = env_int_halo("TL_HALO_DOUBLE", 1) != 0;
     for (; G >= 1; --G) {
         if (allow_res && allow_dbl && halo::smem_bytes(wbytes, G, gbytes2) <= budget) { resident = 1, nbuf = 2; break; }
         if (allow_res && halo::smem_bytes(wbytes, G, gbytes1) <= budget) { resident = 1, nbuf = 1; break; }
@@ -806,6 +856,11 @@ int conv_fwd_halo(const tl_conv_desc& d, cudaStream_t stream, int nsplit) {
     int grid = (P.num_tiles + G - 1) / G;
     if (grid > sms) grid = sms;
     P.rounds = (P.num_tiles + grid * G - 1) / (grid * G);
+    if (P.splits > 1) {
+        grid = P.num_tiles * P.splits, P.rounds = 1, P.splitk_ws = d.splitk_ws;
+        TL_CUDA_CHECK(cudaMemsetAsync(d.splitk_ws, 0, sizeof(float) * (size_t)d.n_out * d.c_out, stream));
+    }
+    auto run = [&]() -> int {
 #define TL_HALO_LAUNCH2(NS, GG, FF) return P.resident ? halo::launch<NS, GG, true, FF>(d, P, grid, smem, stream) : halo::launch<NS, GG, false, FF>(d, P, grid, smem, stream)
 #define TL_HALO_LAUNCH(NS, GG, FHI, FLO) if (fill == FHI) { TL_HALO_LAUNCH2(NS, GG, FHI); } else { TL_HALO_LAUNCH2(NS, GG, FLO); }
     if (nsplit == 1) {
@@ -822,6 +877,15 @@ int conv_fwd_halo(const tl_conv_desc& d, cudaStream_t stream, int nsplit) {
     }
 #undef TL_HALO_LAUNCH2
 #undef TL_HALO_LAUNCH
+    };
+    const int rc = run();
+    if (rc != TL_OK || P.splits == 1) return rc;
+    const int64_t total = (int64_t)d.n_out * d.c_out;
+    const unsigned eg = (unsigned)((total + 255) / 256 > sms * 8 ? sms * 8 : (total + 255) / 256);
+    if (nsplit == 1) halo::k_splitk_epilogue_p<tc::FMT_F16><<<eg, 256, 0, stream>>>(d, d.splitk_ws);
+    else halo::k_splitk_epilogue_p<tc::FMT_F16X2><<<eg, 256, 0, stream>>>(d, d.splitk_ws);
+    TL_LAUNCH_CHECK();
+    return TL_OK;
 }
 
 }  // namespace tl

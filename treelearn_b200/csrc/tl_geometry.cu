@@ -181,17 +181,25 @@ __global__ void k_level_emit(const uint64_t* __restrict__ fkeys, const int* __re
                              int64_t down_stride, int64_t up_stride, uint64_t* __restrict__ ckeys,
                              int* __restrict__ ccoords, int* __restrict__ down_index, uint32_t* __restrict__ down_mask,
                              int* __restrict__ up_index, uint32_t* __restrict__ up_mask) {
-    int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    const uint64_t key = fkeys[j];
-    uint64_t pk;
-    if (!parent_of(key, cshape, pk)) return;  // dropped by the odd-edge rule (App. A.3): no pair
-    const int par = scan[j] - 1;
+    const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    // no early exit: the per-tile offset masks are OR-ed warp-wide first (one atomic per warp and mask word instead of one per
+    // voxel: 128 voxels hit the same word)
+    const uint64_t key = j < n ? fkeys[j] : 0;
+    uint64_t pk = 0;
+    const bool live = j < n && parent_of(key, cshape, pk);  // else dropped by the odd-edge rule (App. A.3): no pair
+    const int par = live ? scan[j] - 1 : 0;
     const int kappa = (int)(key & 7);
+    const unsigned bit = live ? 1u << kappa : 0u;
+    const int lane = threadIdx.x & 31;
+    const int dword = live ? par / TL_TILE_ROWS : -1;
+    const unsigned grp = __match_any_sync(0xffffffffu, dword);
+    const unsigned dbits = __reduce_or_sync(grp, bit);
+    if (live && lane == __ffs(grp) - 1) atomicOr(&down_mask[dword], dbits);
+    const unsigned ubits = __reduce_or_sync(0xffffffffu, bit);     // 32 consecutive rows share one 128-row tile
+    if (lane == 0 && ubits) atomicOr(&up_mask[j / TL_TILE_ROWS], ubits);
+    if (!live) return;
     down_index[kappa * down_stride + par] = (int)j;
     up_index[kappa * up_stride + j] = par;
-    atomicOr(&down_mask[par / TL_TILE_ROWS], 1u << kappa);
-    atomicOr(&up_mask[j / TL_TILE_ROWS], 1u << kappa);
     if (j == 0 || scan[j - 1] != scan[j]) {  // first child of this parent
         ckeys[par] = pk;
         int b, x, y, z;
