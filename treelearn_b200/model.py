@@ -80,10 +80,13 @@ class TreeLearn(nn.Module):
         self.max_num_points_per_voxel = max_num_points_per_voxel
         # 'fp32' (SIMT, exact-ish) | 'tf32' | 'f16' (tcgen05, fp16 operands) | 'f16x2' (tcgen05, two-term fp16 split of both
         # operands = fp32-equivalent products: the reference's inference arithmetic is fp32)
+        # 'mixed': f16x2 on the first `split_levels` U-Net levels (where 94 % of the voxels and of the output error live), f16
+        # below; the activated tensors change format at that one level boundary (two small elementwise passes)
         self.mode = mode
-        if mode not in ('fp32', 'tf32', 'f16', 'f16x2'):
+        if mode not in ('fp32', 'tf32', 'f16', 'f16x2', 'mixed'):
             raise ValueError(f'unknown mode {mode!r}')
-        if mode in ('f16', 'f16x2') and channels % 32 != 0:
+        self.split_levels = {'f16x2': num_blocks, 'mixed': int(kwargs.get('split_levels', os.environ.get('TL_SPLIT_LEVELS', '2')))}.get(mode, 0)
+        if mode in ('f16', 'f16x2', 'mixed') and channels % 32 != 0:
             raise ValueError(f"mode={mode!r} needs channels % 32 == 0 (every conv must take the tcgen05 path)")
         self.planes = [channels * (i + 1) for i in range(num_blocks)]
         self._norm = functools.partial(nn.BatchNorm1d, eps=BN_EPS, momentum=BN_MOMENTUM)
@@ -153,20 +156,28 @@ class TreeLearn(nn.Module):
 
     # ---- weight packing (eval): BN folded to scale/shift, conv weights to the kernel layout -------
     def _version_key(self):
-        return (self.mode, self.input_conv._modules['0'].weight.device,
+        return (self.mode, self.split_levels, self.input_conv._modules['0'].weight.device,
                 tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers())))
 
     def _pack(self):
         key = self._version_key()
         if self._packed is not None and self._packed['key'] == key:
             return self._packed
-        tf32 = self.mode in ('tf32', 'f16')
-        half = self.mode == 'f16'
-        ts = 2 if self.mode == 'f16x2' else (1 if (half and sparse.USE_TS) else 0)   # tensor-memory-A kernel: (hi, lo) terms
+        tf32 = self.mode in ('tf32', 'f16', 'mixed')
+        half = self.mode in ('f16', 'mixed')
+        half_modes = self.mode in ('f16', 'f16x2', 'mixed')
+
+        def ts_of(name):   # (hi, lo) terms of the module's level: 2 = f16x2, 1 = f16, 0 = not a half mode
+            if not half_modes:
+                return 0
+            if name.split('.').count('u') < self.split_levels:
+                return 2
+            return 1 if sparse.USE_TS else 0
         pk = {'key': key}
         with torch.no_grad():
             for name, m in self.named_modules():
                 if isinstance(m, SparseConvWeight):
+                    ts = ts_of(name)
                     w = m.weight.detach().float()
                     co, ci = m.out_channels, m.in_channels
                     w = w.reshape(co, -1, ci)
@@ -287,14 +298,21 @@ class TreeLearn(nn.Module):
 
     def _run_backbone(self, vfeats, levels):
         pk = self._pack()
-        mode = {'fp32': _lib.MODE_FP32, 'tf32': _lib.MODE_TF32, 'f16': _lib.MODE_F16, 'f16x2': _lib.MODE_F16X2}[self.mode]
+        mode = self._mode_id(0)
         g0 = levels[0]
         x, xa = sparse.conv([Seg(vfeats, pk['input_conv.0'][0], g0.nbr, g0.nbr_mask)], g0.n, self.planes[0], mode,
                             raw=True, act1=pk['unet.blocks.block0.conv_branch.0'])
-        return self._run_ublock('unet', 0, x, xa, levels, pk, mode, pk['output_layer.0'])
+        return self._run_ublock('unet', 0, x, xa, levels, pk, pk['output_layer.0'])
 
-    def _run_ublock(self, p, l, x, xa, levels, pk, mode, ret_act):
+    def _mode_id(self, l):
+        """Kernel mode of U-Net level l."""
+        if self.mode in ('f16', 'f16x2', 'mixed'):
+            return _lib.MODE_F16X2 if l < self.split_levels else _lib.MODE_F16
+        return {'fp32': _lib.MODE_FP32, 'tf32': _lib.MODE_TF32}[self.mode]
+
+    def _run_ublock(self, p, l, x, xa, levels, pk, ret_act):
         """x: raw features [n_l, C_l]; xa = relu(bn(x)) for blocks.block0; returns relu(ret_bn(level output))."""
+        mode = self._mode_id(l)
         g, c, n = levels[l], self.planes[l], levels[l].n
         nbr = lambda src, w: Seg(src, w, g.nbr, g.nbr_mask)   # noqa: E731
         conv = functools.partial(sparse.conv, n_out=n, c_out=c, mode=mode)
@@ -311,7 +329,12 @@ class TreeLearn(nn.Module):
         gn, cn = levels[l + 1], self.planes[l + 1]
         d, da = sparse.conv([Seg(za_down, pk[p + '.conv.2'][0], g.down_index, g.down_mask)], gn.n, cn, mode,
                             raw=True, act1=pk[p + '.u.blocks.block0.conv_branch.0'])
-        ua = self._run_ublock(p + '.u', l + 1, d, da, levels, pk, mode, pk[p + '.deconv.0'])
+        child = self._mode_id(l + 1)
+        if child != mode:      # f16x2 -> f16 at this level boundary: hi + lo -> one fp16 term (the fp32 stream `d` is format-free)
+            da = sparse.split_to_half(da)
+        ua = self._run_ublock(p + '.u', l + 1, d, da, levels, pk, pk[p + '.deconv.0'])
+        if child != mode:      # the child's fp16 output as a (hi, lo = 0) operand of this level's inverse conv
+            ua = sparse.half_to_split(ua)
         e, ea = conv([Seg(ua, pk[p + '.deconv.2'][0], g.up_index, g.up_mask)], raw=True, act1=(s_cat[c:], t_cat[c:]))
         wa, wi = pk[t0 + '.conv_branch.2'], pk[t0 + '.i_branch.0']
         ha = conv([nbr(za_tail, wa[0]), nbr(ea, wa[1])], act1=pk[t0 + '.conv_branch.3'])
@@ -333,7 +356,7 @@ class TreeLearn(nn.Module):
             feats = voxel_out.float()[v2p]
             return {'backbone_feats': feats, 'semantic_prediction_logits': self.semantic_linear(feats),
                     'offset_predictions': self.offset_linear(feats)}
-        feats, logits, offs = sparse.heads(voxel_out, v2p, self._pack(), split=self.mode == 'f16x2')
+        feats, logits, offs = sparse.heads(voxel_out, v2p, self._pack(), split=self._mode_id(0) == _lib.MODE_F16X2)
         return {'backbone_feats': feats, 'semantic_prediction_logits': logits, 'offset_predictions': offs}
 
     def get_loss(self, model_output, semantic_labels, offset_labels, masks_off, masks_sem, **kwargs):

@@ -360,6 +360,21 @@ def from_split(x):
     return from_p((v[:, :, 0] + v[:, :, 1]).reshape(r, c2 // 2))
 
 
+def split_to_half(x):
+    """f16x2 operand format [rows, 2C] (per 32-channel block: 32 hi halves, 32 lo halves) -> fp16 [rows, C] = fp16(hi + lo),
+    same P-layout channel order."""
+    r, c2 = x.shape
+    v = x.reshape(r, c2 // 64, 2, 32)
+    return (v[:, :, 0].float() + v[:, :, 1].float()).half().reshape(r, c2 // 2).contiguous()
+
+
+def half_to_split(x):
+    """fp16 [rows, C] -> f16x2 operand format [rows, 2C] with zero lo terms."""
+    r, c = x.shape
+    v = x.reshape(r, c // 32, 1, 32)
+    return torch.cat([v, torch.zeros_like(v)], 2).reshape(r, 2 * c).contiguous()
+
+
 SPLITK_MAX_ROWS = 2 * 148 * TILE_ROWS   # below two waves of 128-row tiles the library may split K over CTAs
 PROFILE = None   # bench.py sets this to a list: every conv launch appends (start_evt, end_evt, alg_bytes, flops)
 
