@@ -710,23 +710,9 @@ __global__ void __launch_bounds__(HB_THREADS) k_halo_build(const int32_t* __rest
         const int v = table[t * PER + i];
         if (v >= 0) list[at++] = v;
     }
-    int m = 1;
-    while (m < total) m <<= 1;
-    for (int i = total + t; i < m; i += HB_THREADS) list[i] = 0x7fffffff;
     __syncthreads();
-    for (int k2 = 2; k2 <= m; k2 <<= 1) {        // bitonic sort, ascending
-        for (int j = k2 >> 1; j > 0; j >>= 1) {
-            for (int i = t; i < m; i += HB_THREADS) {
-                const int ixj = i ^ j;
-                if (ixj > i) {
-                    const int a = list[i], b = list[ixj];
-                    const bool up = (i & k2) == 0;
-                    if ((a > b) == up) list[i] = b, list[ixj] = a;
-                }
-            }
-            __syncthreads();
-        }
-    }
+    // (no sort: list order = hash-slot order.  Positions are free since the class swizzle; ascending row ids only made the
+    // halo fetch walk DRAM in order, and the ~230 rows of a tile sit in a few KB-sized runs either way)
     // ---- positions: rows whose class has bit 2 clear take the even positions 2, 4, ..., the others the odd ones 1, 3, ...
     for (int i = t; i < total; i += HB_THREADS) cls_list[i] = (unsigned char)(__ldg(keys + list[i]) & 7u);
     __syncthreads();

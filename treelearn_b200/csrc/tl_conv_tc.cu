@@ -733,10 +733,13 @@ int conv_fwd_tc(const tl_conv_desc& d, cudaStream_t stream, bool half) {
             if (d.seg[s].c_in % 64 != 0) bkc = 32;
     }
     const int row_bytes = half ? 2 * bkc : 128;
-    static int num_sms = 0, smem_budget = 0, split_target = 0;
+    // per device: SM count and the kernels' dynamic shared-memory attribute (function attributes are per device)
+    static int num_sms_dev[16] = {0}, smem_budget = 0, split_target = 0;
+    int dev = 0;
+    TL_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 16) return TL_ERR_UNSUPPORTED;
+    int& num_sms = num_sms_dev[dev];
     if (!num_sms) {
-        int dev = 0;
-        TL_CUDA_CHECK(cudaGetDevice(&dev));
         TL_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
         TL_CUDA_CHECK(cudaFuncSetAttribute(tc::k_conv_tc<4, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         TL_CUDA_CHECK(cudaFuncSetAttribute(tc::k_conv_tc<2, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
