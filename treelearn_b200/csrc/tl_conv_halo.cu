@@ -677,11 +677,11 @@ __global__ void __launch_bounds__(HB_THREADS) k_halo_build(const int32_t* __rest
     }
     __syncthreads();
     if (is_left) lane_of[t] = hole_list[pl];
-    // compact the occupied slots: each thread owns HB_TABLE / HB_THREADS consecutive slots
+    // compact the occupied slots: each thread owns the HB_TABLE / HB_THREADS slots t, t + 256, ...
     constexpr int PER = HB_TABLE / HB_THREADS;
     int mine = 0;
 #pragma unroll
-    for (int i = 0; i < PER; ++i) mine += table[t * PER + i] >= 0;
+    for (int i = 0; i < PER; ++i) mine += table[i * HB_THREADS + t] >= 0;      // interleaved slots: conflict-free (t * PER + i was 16-way)
     int incl = mine;
     for (int off = 1; off < 32; off <<= 1) {
         const int v = __shfl_up_sync(0xffffffffu, incl, off);
@@ -707,7 +707,7 @@ __global__ void __launch_bounds__(HB_THREADS) k_halo_build(const int32_t* __rest
     int at = warp_tot[t >> 5] + incl - mine;
 #pragma unroll
     for (int i = 0; i < PER; ++i) {
-        const int v = table[t * PER + i];
+        const int v = table[i * HB_THREADS + t];
         if (v >= 0) list[at++] = v;
     }
     __syncthreads();
