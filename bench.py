@@ -483,7 +483,8 @@ def run_b200(args):
             dist.destroy_process_group()
         return
     value = n_vox_total / (ms_res * 1e-3) / 1e6
-    h2d = sum(v.numel() * v.element_size() for v in host.values() if torch.is_tensor(v))
+    # segment_tile copies coords and input_feats once; batch_ids of a one-tile batch are filled on the device (model.py)
+    h2d = sum(host[k].numel() * host[k].element_size() for k in ('coords', 'input_feats'))
     line = {
         'metric': METRIC, 'value': round(value, 2), 'unit': 'Mvoxels/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': round(ms_res, 3), 'higher_is_better': True, 'scaling': 'weak',

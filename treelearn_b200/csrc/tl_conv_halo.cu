@@ -14,13 +14,20 @@
 //     layer's weights fit, they stay resident;
 //   * per (segment, 32-channel block) = K-slice: the 4 warps copy the halo rows' 64 B (f16) / 128 B (f16x2) slices with
 //     cp.async (one request per distinct row instead of 6.9), then for each of the 27 offsets every lane reads ITS row's
-//     slice from shared memory (4 / 8 LDS.128, XOR-swizzled rows, absent neighbour = the zero row 0) and writes it to
-//     tensor memory with one tcgen05.st.32x32b.x16 per term: lane = row, 16 columns = 32 fp16 K values;
+//     slice from shared memory (4 / 8 LDS.128, absent neighbour = predicated off) and writes it to tensor memory with one
+//     tcgen05.st.32x32b.x16 per term: lane = row, 16 columns = 32 fp16 K values;
+//   * the reads are bank-conflict free by construction ("class swizzle", see tl_halo_build below): rows are stored
+//     XOR-swizzled by the voxel's parity class and the tile's rows are permuted over the lanes so that the 8 lanes of an
+//     LDS.128 phase hold 8 different classes -- for every one of the 27 offsets at once;
 //   * the MMA warp issues TS-form tcgen05.mma (A from tensor memory: 16.6 cycles per N = 32, K = 16 instead of 41 for
 //     the shared-memory form, profiles/r02_ts_probe.txt) for a FILL of chunks per barrier round trip (4 chunks in f16, 2
 //     in f16x2; two fills in flight), one tcgen05.commit per fill;
-//   * epilogue as in tl_conv_grp.cu: tcgen05.ld.16x256b, residual / scale / shift / ReLU, P-layout vector stores.
-// Shared-memory traffic is the floor now: 128 rows x 64 B x 27 offsets = 221 KB per tile and K-slice.
+//   * epilogue as in tl_conv_grp.cu: tcgen05.ld.16x256b, residual / scale / shift / ReLU, P-layout vector stores (lanes map
+//     back to tile rows through the permutation);
+//   * levels with fewer tiles than half the SMs split the K-slices of a tile over CTAs (fp32 red.add into a scratch tensor,
+//     k_splitk_epilogue_p applies the epilogue).
+// The floor of this design is the SM's load/store datapath: every A byte crosses it twice (LDS shared memory -> registers,
+// tcgen05.st registers -> tensor memory), 2 x 221 KB per tile and K-slice in f16 (profiles/r02_conv_history.md).
 //
 // Tensors use the P-layout channel order of treelearn_b200/sparse.py (see tl_conv_grp.cu); weights are the same
 // [n_off][c_in/32][(hi, lo)][C_out][32] SWIZZLE_64B images (sparse.pack_weight_grp).

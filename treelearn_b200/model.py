@@ -228,6 +228,10 @@ class TreeLearn(nn.Module):
 
     def forward_backbone(self, coords, input_feats, batch_ids, batch_size, **kwargs):
         dev = torch.device('cuda', torch.cuda.current_device())
+        if int(batch_size) == 1 and batch_ids.device.type == 'cpu':
+            # one tile per batch (the pipeline's setting, configs/pipeline/pipeline.yaml:15-17): every id is 0 by construction
+            # of collate_fn (dataset.py:214-226) -- fill on the device instead of copying 8 B per point over PCIe
+            batch_ids = torch.zeros(batch_ids.shape[0], dtype=torch.int64, device=dev)
         coords, input_feats, batch_ids = (t.to(dev, non_blocking=True) for t in (coords, input_feats, batch_ids))
         vfeats, vcoords, keys, v2p = sparse.voxelize(
             coords, input_feats, batch_ids, batch_size, self.voxel_size, self.use_coords, self.use_feats,

@@ -275,10 +275,14 @@ def segment_tile(model, batch, grouping_cfg):
     """Public per-tile call used by bench.py's e2e leg: host batch dict in (pinned or pageable), network forward,
     offset-shifted clustering and remaining-point assignment on the device, instance labels out on the host."""
     with torch.no_grad():
-        out = model(batch, return_loss=False)
-        dev = out['offset_predictions'].device
-        coords = batch['coords'].to(dev, non_blocking=True)
-        vert = batch['input_feats'].to(dev, non_blocking=True)[:, -1]
+        # every input crosses PCIe once: the device copies feed both the network and the clustering stage
+        dev = torch.device('cuda', torch.cuda.current_device())
+        on_dev = dict(batch)
+        on_dev['coords'] = batch['coords'].to(dev, non_blocking=True)
+        on_dev['input_feats'] = batch['input_feats'].to(dev, non_blocking=True)
+        on_dev['_source_coords_id'] = id(batch['coords'])       # unknown keys are ignored by the model (tree_learn.py:84)
+        out = model(on_dev, return_loss=False)
+        coords, vert = on_dev['coords'], on_dev['input_feats'][:, -1]
         labels, n_clusters = instances_cuda(coords, out['offset_predictions'], out['semantic_prediction_logits'], vert,
                                             grouping_cfg)
         return labels.to(torch.int32).cpu().numpy(), n_clusters

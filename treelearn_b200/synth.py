@@ -223,7 +223,8 @@ class TrainedLikeOutputs(torch.nn.Module):
 
     def forward(self, batch, return_loss=False):
         out = dict(self.model(batch, return_loss=return_loss))
-        c_off, c_sem = self._corr[id(batch['coords'])]
+        key = id(batch['coords'])
+        c_off, c_sem = self._corr[key if key in self._corr else batch.get('_source_coords_id')]
         out['offset_predictions'] = out['offset_predictions'] + c_off
         out['semantic_prediction_logits'] = out['semantic_prediction_logits'] + c_sem
         return out
