@@ -78,7 +78,18 @@ def build_levels(keys, coords, spatial_shape, num_levels, subm=True):
     if subm:
         for lv in levels:
             build_subm_rulebook(lv)
+        read_halo_sizes(levels)
     return levels
+
+
+def read_halo_sizes(levels):
+    """One host read for the largest halo list of EVERY level (instead of one synchronisation per level in the middle of the
+    conv stream, where the host would wait for all queued convolutions before it can enqueue the next level's)."""
+    halos = [lv.nbr.halo for lv in levels if lv.nbr is not None and getattr(lv.nbr, 'halo', None) is not None
+             and lv.nbr.halo._umax is None]
+    if halos:
+        for h, v in zip(halos, torch.cat([h.max_cnt for h in halos]).tolist()):
+            h._umax = int(v)
 
 
 def _extend_levels(levels, num_levels):
