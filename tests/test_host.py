@@ -68,3 +68,31 @@ def test_no_cpu_fallback():
     with pytest.raises(Exception):
         with torch.no_grad():
             net(batch, return_loss=False)
+
+
+def test_operand_format_conversions_round_trip_on_cpu():
+    """The two elementwise passes at the level boundary of mode 'mixed' (sparse.split_to_half / half_to_split) against the
+    reference conversions to_split / to_p / from_split."""
+    import torch
+    from treelearn_b200 import sparse
+    x = torch.randn(7, 96, generator=torch.Generator().manual_seed(0))
+    h = sparse.split_to_half(sparse.to_split(x))                    # f16x2 operand -> one fp16 term, P-layout kept
+    assert h.dtype == torch.float16 and h.shape == (7, 96)
+    assert torch.equal(h, sparse.to_p(x).half())                    # hi + lo re-rounds to fp16(x) exactly
+    s = sparse.half_to_split(h)
+    assert s.shape == (7, 192)
+    assert torch.equal(sparse.from_split(s), sparse.from_p(h.float()))   # lo terms are zero
+
+
+def test_bench_secondary_kernel_table_parses_the_committed_launch_list():
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location('bench_mod', os.path.join(root, 'bench.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    sec = mod.secondary_kernels(6455.6)
+    names = [k['kernel'] for k in sec['kernels']]
+    for want in ('k_subm_probe', 'k_halo_build', 'k_heads', 'k_cc_link', 'k_knn_vote', 'k_emit_voxels'):
+        assert want in names
+    assert all(0 < k['frac'] < 1 and k['us_per_step'] > 0 for k in sec['kernels'])
