@@ -458,21 +458,34 @@ def run_b200(args):
     # the single-term mode beside the headline (same weights, same tile, same trained-like correction)
     fast = mixed = None
     if args.mode == 'f16x2':
+        def conv_stack(prof):    # roofline of the conv launches of the timed steps of a secondary mode, like `roofline`
+            per = len(prof) // (args.steps + args.warmup)
+            tp = prof[args.warmup * per:]
+            ms = sum(a.elapsed_time(b) for a, b, _, _, _ in tp)
+            by = sum(p[2] for p in tp)
+            return {'kernel_ms_per_step': round(ms / args.steps, 3), 'alg_bytes_per_step': int(by / args.steps),
+                    'achieved': round(by / (ms * 1e-3) / 1e9, 1), 'unit': 'GB/s', 'frac': round(by / (ms * 1e-3) / 1e9 / peak, 4)}
+
         fnet = synth.TrainedLikeOutputs(make_net('f16')).eval()
         fnet._corr = net._corr
+        sparse.PROFILE = []
         ms_fast = timed(lambda: step_resident(fnet), args.steps, args.warmup)
+        fast_conv, sparse.PROFILE = conv_stack(sparse.PROFILE), None
         fast = {'mode': 'f16', 'dtype': DTYPE_TEXT['f16'], 'ms_per_step': round(ms_fast, 3),
                 'value': round(n_vox_total / (ms_fast * 1e-3) / 1e6, 2), 'unit': 'Mvoxels/s',
+                'conv_stack': fast_conv,
                 'note': 'outside the 1e-3 offset tolerance at metre-scale outputs: see parity.fast_mode'}
         del fnet
         # two fp16 terms on U-Net levels 0-1 only (94 % of the voxels), one term on levels 2-6: inside the tolerance with a
         # ~5x margin (parity.mixed_mode), reported beside the all-levels f16x2 headline
         mnet = synth.TrainedLikeOutputs(make_net('mixed')).eval()
         mnet._corr = net._corr
+        sparse.PROFILE = []
         ms_mixed = timed(lambda: step_resident(mnet), args.steps, args.warmup)
+        mixed_conv, sparse.PROFILE = conv_stack(sparse.PROFILE), None
         mixed = {'mode': 'mixed', 'dtype': DTYPE_TEXT['mixed'], 'ms_per_step': round(ms_mixed, 3),
                  'value': round(n_vox_total / (ms_mixed * 1e-3) / 1e6, 2), 'unit': 'Mvoxels/s',
-                 'note': 'see parity.mixed_mode for its error against the fp32 oracle'}
+                 'conv_stack': mixed_conv, 'note': 'see parity.mixed_mode for its error against the fp32 oracle'}
         del mnet
 
     cluster = cluster_record(args, resident, dev) if (rank == 0 and not args.no_cluster) else None
