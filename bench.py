@@ -181,7 +181,8 @@ def plot_record(net, args, world, rank, dev, dist):
     (fwd, ag, mg, cl, tot), npts, ncl = timed(world, 2)
     rec = {'workload': 'cfg4_plot64: one synthetic plot (63 m edge) cut into 64 overlapping 35 m tiles (inner 8 m, stride 0.5), '
                        'tiles sharded over the ranks, all-gather of the inner rows, replicated merge + DBSCAN-equivalent '
-                       'clustering + kNN assignment', 'scaling': 'strong', 'tiles': len(tiles), 'tile_points_total': n_points,
+                       'clustering + kNN assignment; a rank collates up to 6 M points (8 tiles) into one network forward',
+           'scaling': 'strong', 'tiles': len(tiles), 'tile_points_total': n_points,
            'merged_points': npts, 'clusters': ncl, 'n_gpus': world, 's_end_to_end': round(tot / 1e3, 4),
            'forward_ms': round(fwd, 2), 'allgather_ms': round(ag, 2), 'merge_ms': round(mg, 2), 'cluster_knn_ms': round(cl, 2),
            'Mpoints_per_s': round(n_points / (tot * 1e-3) / 1e6, 2), 'api': 'treelearn_b200.dist.segment_plot(model, tiles, grouping_cfg)'}

@@ -110,3 +110,30 @@ def test_segment_points_stage_by_stage_vs_oracle(return_type):
         ok = np.repeat(~missing, np.diff(trace.offsets))
         assert np.array_equal(res['instance_preds'][trace.indices][ok], np.repeat(vox, np.diff(trace.offsets))[ok])
         assert res['instance_preds'].shape == (len(data),) and res['instance_preds'].min() >= 0
+
+
+@pytest.mark.gpu
+def test_segment_plot_several_tiles_per_forward_equals_one_tile_per_forward():
+    """dist.segment_plot runs a rank's tiles in chunks of several tiles per network forward (one batch element per tile);
+    the merged plot and its instance labels are the same as with one tile per forward (the reference's batch size 1)."""
+    from treelearn_b200 import TreeLearn
+    from treelearn_b200 import dist as tdist
+    g = SimpleNamespace(tree_conf_thresh=0.5, tau_vert=0.6, tau_off=4, tau_group=0.15, tau_min=50, use_hdbscan=False)
+    forest = synth.synth_forest(edge=24.0, n_trees=30, seed=7)
+    xyz = torch.from_numpy(forest['coords'])
+    tiles = []
+    for cx in (-6.0, 0.0, 6.0):
+        for cy in (-6.0, 0.0, 6.0):                      # 3 x 3 tiles of 14 m with an 8 m inner square: real overlaps
+            sel = (((xyz[:, 0] - cx).abs() < 7.0) & ((xyz[:, 1] - cy).abs() < 7.0)).numpy()
+            t = {k: (v[sel] if hasattr(v, 'shape') and len(v) == len(xyz) else v) for k, v in forest.items()}
+            t['coords'] = (t['coords'] - [cx, cy, 0.0]).astype('float32')
+            t['centre'] = (forest['centre'] + [cx, cy, 0.0]).astype('float32')
+            tiles.append(synth.make_batch([t], inner_edge=8.0))
+    torch.manual_seed(0)
+    net = synth.randomize_bn_stats(TreeLearn(use_feats=False, use_coords=False, spatial_shape=[500, 500, 1000],
+                                             mode='f16x2')).cuda().eval()
+    c1, l1, n1 = tdist.segment_plot(net, tiles, g, points_per_forward=1)              # one tile per forward
+    c4, l4, n4 = tdist.segment_plot(net, tiles, g, points_per_forward=10 ** 9)        # all nine tiles in one forward
+    c2, l2, n2 = tdist.segment_plot(net, tiles, g, points_per_forward=int(2.5 * tiles[0]['coords'].shape[0]))
+    assert torch.equal(c1, c4) and torch.equal(c1, c2)
+    assert torch.equal(l1, l4) and torch.equal(l1, l2) and int(n1) == int(n4) == int(n2)

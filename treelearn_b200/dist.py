@@ -57,10 +57,29 @@ def allgather_rows_known(t, sizes, group=None):
     return torch.cat([out[r * m:r * m + s] for r, s in enumerate(sizes)], dim=0)
 
 
-def segment_plot(model, tiles, grouping_cfg, group=None, marks=None):
+def _forward_chunk(model, chunk, dev):
+    """One network forward over several tiles as ONE batch (tile = batch element, like a DataLoader batch of the reference's
+    collate_fn, dataset.py:214-226) and the inner-square rows [x, y, z, logits(2), offsets(3), verticality] of all of them.
+    A 35 m tile of ~0.7 M points spends about half of its forward in per-launch floors of the deep U-Net levels (~40 us x
+    66 conv launches) and host synchronisations of the level builder; several tiles per forward share them."""
+    coords = torch.cat([b['coords'].to(dev, non_blocking=True) for b in chunk])
+    feats = torch.cat([b['input_feats'].to(dev, non_blocking=True) for b in chunk])
+    counts = [int(b['coords'].shape[0]) for b in chunk]
+    ids = torch.repeat_interleave(torch.arange(len(chunk), device=dev), torch.tensor(counts, device=dev), output_size=sum(counts))
+    batch = {'coords': coords, 'input_feats': feats, 'batch_ids': ids, 'batch_size': len(chunk),
+             '_source_coords_id': [id(b['coords']) for b in chunk]}          # unknown keys are ignored by the model
+    out = model(batch, return_loss=False)
+    inner = torch.cat([b['masks_inner'] for b in chunk]).to(dev, non_blocking=True)
+    centers = torch.cat([b['centers'].to(dev, non_blocking=True) for b in chunk])
+    xyz = (coords + centers)[inner]
+    return torch.cat([xyz, out['semantic_prediction_logits'][inner], out['offset_predictions'][inner], feats[inner][:, -1:]], dim=1)
+
+
+def segment_plot(model, tiles, grouping_cfg, group=None, marks=None, points_per_forward=6_000_000):
     """Whole-plot inference (BASELINE.json config 4): `tiles` is the same list of host batch dicts on every rank.
     Returns (merged coords [P,3], instance labels [P], n_clusters) as CUDA tensors, identical on every rank.
-    `marks` (optional list) receives (name, cuda event) pairs at the stage boundaries: forward, allgather, merge, cluster."""
+    `marks` (optional list) receives (name, cuda event) pairs at the stage boundaries: forward, allgather, merge, cluster.
+    A rank runs its tiles in chunks of up to `points_per_forward` points per network forward (at least one tile)."""
     from . import pipeline
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -83,13 +102,15 @@ def segment_plot(model, tiles, grouping_cfg, group=None, marks=None):
     mark('start')
     with torch.no_grad():
         model.eval()
-        for i in mine:
-            b = tiles[i]
-            out = model(b, return_loss=False)
-            inner = b['masks_inner'].to(dev, non_blocking=True)
-            xyz = (b['coords'] + b['centers']).to(dev, non_blocking=True)[inner]
-            rows.append(torch.cat([xyz, out['semantic_prediction_logits'][inner], out['offset_predictions'][inner],
-                                   b['input_feats'].to(dev, non_blocking=True)[inner][:, -1:]], dim=1))
+        chunk, pts = [], 0
+        for i in mine + [None]:
+            n = 0 if i is None else int(tiles[i]['coords'].shape[0])
+            if chunk and (i is None or pts + n > points_per_forward):
+                rows.append(_forward_chunk(model, chunk, dev))
+                chunk, pts = [], 0
+            if i is not None:
+                chunk.append(tiles[i])
+                pts += n
     local = torch.cat(rows) if rows else torch.zeros((0, 9), device=dev)
     mark('forward')
     allrows = allgather_rows_known(local.contiguous(), sizes, group)          # the one collective of the inference path

@@ -224,7 +224,12 @@ class TrainedLikeOutputs(torch.nn.Module):
     def forward(self, batch, return_loss=False):
         out = dict(self.model(batch, return_loss=return_loss))
         key = id(batch['coords'])
-        c_off, c_sem = self._corr[key if key in self._corr else batch.get('_source_coords_id')]
+        src = key if key in self._corr else batch.get('_source_coords_id')
+        if isinstance(src, (list, tuple)):          # several prepared tiles collated into one batch
+            c_off = torch.cat([self._corr[k][0] for k in src])
+            c_sem = torch.cat([self._corr[k][1] for k in src])
+        else:
+            c_off, c_sem = self._corr[src]
         out['offset_predictions'] = out['offset_predictions'] + c_off
         out['semantic_prediction_logits'] = out['semantic_prediction_logits'] + c_sem
         return out
